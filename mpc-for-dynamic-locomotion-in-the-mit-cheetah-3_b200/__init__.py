@@ -1,0 +1,8 @@
+"""B200-native batched convex-MPC solver for the Lite3 quadruped (hot path of the
+reference's ``src/mpc.py``).  Import through :mod:`mpc_b200` (the directory name is
+not a Python identifier) or ``importlib.import_module``."""
+from .gait import GaitPlan, GAITS, LEGS, stance_bits          # noqa: F401
+from .assembly import (desired_trajectory, assemble_tick,      # noqa: F401
+                       reference_velocity, pack_problem)
+
+__version__ = "0.1.0"

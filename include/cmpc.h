@@ -1,0 +1,137 @@
+/* cmpc.h - C ABI of the B200-native batched convex-MPC solver.
+ *
+ * Drop-in boundary for the hot path of the reference's `MPC` class
+ * (Emilianogith/MPC-for-dynamic-locomotion-in-the-MIT-cheetah-3, src/mpc.py).  The
+ * reference has no FFI layer of its own: `MPC.__init__` builds the QP with CasADi
+ * (src/mpc.py:49-173) and `MPC.solve` re-parameterises and solves it with OSQP every
+ * tick (src/mpc.py:242-258).  Each entry point below names the reference code it
+ * replaces.  Python binds these with ctypes.
+ *
+ * Conventions
+ *  - All array arguments of the non-`_host` functions are CUDA DEVICE pointers
+ *    (e.g. torch `tensor.data_ptr()`), fp32, row-major, contiguous, owned by the caller.
+ *  - B problems per call, horizon N fixed per handle.  Legs are FL, FR, HL, HR.
+ *      x0     [B,13]      Theta(3) p(3) omega(3) v(3) g        (src/mpc.py:190-198)
+ *      r      [B,N,4,3]   lever arms foot - com per stage/leg    (src/mpc.py:218-239)
+ *      mask   [B,N] uint8 bit l = 1  <=> leg l in stance at stage i
+ *                         (= 1 - swing_param, src/mpc.py:249-254)
+ *      x_des  [B,N+1,13]  desired trajectory                     (src/mpc.py:202-214)
+ *      mu     [B]         friction coefficient                   (src/mpc.py:33)
+ *      U      [B,N,12]    optimal forces, stage-major (U[:,0,:] is what MPC.solve returns,
+ *                         src/mpc.py:267-278); swing legs are exactly 0
+ *      X      [B,N+1,13]  predicted states (src/mpc.py:265-266), may be NULL
+ *      iters/status [B] int32, pri_res/dua_res [B] fp32; any of them may be NULL
+ *  - Work is enqueued on `stream` (a cudaStream_t passed as void*) and is asynchronous.
+ *  - Every function returns 0 on success or a negative CMPC_ERR_* code; nothing throws.
+ *    `cmpc_last_error()` returns a thread-local description of the last failure.
+ *  - A handle owns the warm-start state (previous primal/dual solution per problem slot,
+ *    src/mpc.py:270-271) and scratch; one handle must not be used from two threads at once.
+ */
+#ifndef CMPC_H
+#define CMPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMPC_VERSION_MAJOR 0
+#define CMPC_VERSION_MINOR 1
+
+enum {
+  CMPC_OK = 0,
+  CMPC_ERR_INVALID = -1,     /* bad argument / unsupported configuration            */
+  CMPC_ERR_CUDA = -2,        /* a CUDA runtime call failed (see cmpc_last_error)    */
+  CMPC_ERR_UNSUPPORTED = -3, /* horizon or weights outside what the kernels cover   */
+  CMPC_ERR_NO_DEVICE = -4    /* no CUDA device: there is NO CPU fallback            */
+};
+
+/* per-problem solver status written to `status` */
+enum {
+  CMPC_STATUS_MAX_ITER = 0,  /* OSQP "maximum iterations reached"                  */
+  CMPC_STATUS_SOLVED = 1,
+  CMPC_STATUS_NAN = -1       /* non-finite data or iterate                          */
+};
+
+/* warm-start policy of cmpc_solve */
+enum {
+  CMPC_WARM_NONE = 0,   /* x = y = 0 every call                                     */
+  CMPC_WARM_PRIMAL = 1, /* reference semantics: previous x unshifted, y = 0
+                           (src/mpc.py:270-271; CasADi passes lam_g0 = 0)           */
+  CMPC_WARM_PRIMAL_DUAL = 2 /* previous x and y                                     */
+};
+
+typedef struct cmpc_config {
+  int32_t N;            /* horizon, src/main.py:41 (`params['N']`)                   */
+  int32_t max_batch;    /* problem slots with persistent warm-start state            */
+  float dt;             /* `world_time_step`, src/mpc.py:31                          */
+  float mass;           /* src/mpc.py:71                                             */
+  float ibody_inv[3];   /* src/mpc.py:73-76                                          */
+  float w[13];          /* state weights, src/mpc.py:121-134                         */
+  float r_weight;       /* force weight, src/mpc.py:121 (0.0)                        */
+  float f_min, f_max;   /* src/mpc.py:45-46                                          */
+  float rho, sigma, alpha;   /* ADMM penalty / prox weight / relaxation              */
+  float eps_abs, eps_rel;    /* OSQP-style termination tolerances (defaults 1e-3)    */
+  int32_t max_iter;     /* src/mpc.py:51 (1000)                                      */
+  int32_t check_every;  /* termination test period                                   */
+  int32_t refresh_every;/* exact recomputation period of the wrench-space gradient   */
+  int32_t warm_mode;    /* CMPC_WARM_*                                               */
+  int32_t device;       /* CUDA device ordinal                                       */
+} cmpc_config;
+
+typedef struct cmpc_handle cmpc_handle;
+
+/* Fill `cfg` with the reference's constants (src/mpc.py:45-46,71-76,121-134; src/main.py:31-46)
+ * for horizon N and the solver defaults of this library. */
+int cmpc_default_config(cmpc_config* cfg, int32_t N, int32_t max_batch);
+
+/* Replaces MPC.__init__ (src/mpc.py:25-173): validates the configuration, precomputes the
+ * horizon Gram matrices, allocates warm-start state on cfg->device. */
+int cmpc_create(const cmpc_config* cfg, cmpc_handle** out);
+int cmpc_destroy(cmpc_handle* h);
+
+/* Replaces `self.opt.set_value(...)` x7 + `self.opt.solve()` + `sol.value(...)`
+ * (src/mpc.py:242-271) for B independent problems occupying warm-start slots
+ * [slot0, slot0+B).  Device pointers. */
+int cmpc_solve(cmpc_handle* h, int32_t B, int32_t slot0,
+               const float* x0, const float* r, const uint8_t* mask, const float* x_des,
+               const float* mu, float* U, float* X, int32_t* iters, float* pri_res,
+               float* dua_res, int32_t* status, void* stream);
+
+/* Same call with HOST pointers: stages through pinned buffers, overlaps H2D / solve / D2H
+ * in chunks on internal streams and returns when the outputs are in host memory.
+ * This is the call the reference-facing Python `MPC.solve` drop-in makes. */
+int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0,
+                    const float* x0, const float* r, const uint8_t* mask, const float* x_des,
+                    const float* mu, float* U, float* X, int32_t* iters, float* pri_res,
+                    float* dua_res, int32_t* status);
+
+/* Exports the dense condensed QP  min 1/2 u'Hu + g'u  over all 12N forces
+ * (H [B,12N,12N], g [B,12N]; rows/columns of swing legs are zero), i.e. what CasADi
+ * derives symbolically from src/mpc.py:64-136 after eliminating X.  Device pointers. */
+int cmpc_condense(cmpc_handle* h, int32_t B, const float* x0, const float* r,
+                  const uint8_t* mask, const float* x_des, float* H, float* g, void* stream);
+
+/* Warm-start state (src/mpc.py:270-271 `set_initial`): forget it for the slots whose
+ * `slot_mask[i] != 0` (all slots if slot_mask == NULL; HOST pointer of max_batch bytes). */
+int cmpc_reset_warm(cmpc_handle* h, const uint8_t* slot_mask);
+/* Copy warm-start forces x [B,N,12] and duals y [B,N,4,5] of slots [slot0, slot0+B)
+ * to / from DEVICE buffers (y may be NULL). */
+int cmpc_get_warm(cmpc_handle* h, int32_t B, int32_t slot0, float* x, float* y, void* stream);
+int cmpc_set_warm(cmpc_handle* h, int32_t B, int32_t slot0, const float* x, const float* y,
+                  void* stream);
+
+/* Number of kernels this library has launched on behalf of `h` since creation. */
+int64_t cmpc_launch_count(const cmpc_handle* h);
+
+/* Horizons the compiled kernels cover: writes up to `cap` values, returns the count. */
+int cmpc_supported_horizons(int32_t* out, int32_t cap);
+
+int cmpc_version(void);               /* major*1000 + minor */
+const char* cmpc_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMPC_H */

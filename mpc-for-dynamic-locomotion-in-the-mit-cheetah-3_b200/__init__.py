@@ -4,5 +4,9 @@ not a Python identifier) or ``importlib.import_module``."""
 from .gait import GaitPlan, GAITS, LEGS, stance_bits          # noqa: F401
 from .assembly import (desired_trajectory, assemble_tick,      # noqa: F401
                        reference_velocity, pack_problem)
+from . import problems                                          # noqa: F401
+from . import _capi                                             # noqa: F401
+from ._capi import CmpcError                                    # noqa: F401
+from .solver import BatchedMPC, MPC, SolveStats                 # noqa: F401
 
 __version__ = "0.1.0"

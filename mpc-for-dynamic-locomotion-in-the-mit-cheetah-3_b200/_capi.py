@@ -1,0 +1,116 @@
+"""ctypes binding of ``csrc/libcmpc.so`` (C ABI declared in ``include/cmpc.h``).
+
+There is no CPU fallback: if the shared library is missing, :func:`lib` raises, and if
+no CUDA device is visible ``cmpc_create`` returns ``CMPC_ERR_NO_DEVICE`` which surfaces
+as :class:`CmpcError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libcmpc.so")
+SOURCES = [os.path.join(CSRC, "cmpc.cu")]
+HEADERS = [os.path.join(CSRC, "cmpc_kernels.cuh"), os.path.join(_ROOT, "include", "cmpc.h")]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+#: every symbol include/cmpc.h declares
+SYMBOLS = ("cmpc_default_config", "cmpc_create", "cmpc_destroy", "cmpc_solve", "cmpc_solve_host",
+           "cmpc_condense", "cmpc_reset_warm", "cmpc_get_warm", "cmpc_set_warm",
+           "cmpc_launch_count", "cmpc_supported_horizons", "cmpc_version", "cmpc_last_error")
+
+
+class CmpcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"cmpc error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    """Mirror of ``struct cmpc_config``."""
+    _fields_ = [("N", C.c_int32), ("max_batch", C.c_int32), ("dt", C.c_float), ("mass", C.c_float),
+                ("ibody_inv", C.c_float * 3), ("w", C.c_float * 13), ("r_weight", C.c_float),
+                ("f_min", C.c_float), ("f_max", C.c_float), ("rho", C.c_float),
+                ("sigma", C.c_float), ("alpha", C.c_float), ("eps_abs", C.c_float),
+                ("eps_rel", C.c_float), ("max_iter", C.c_int32), ("check_every", C.c_int32),
+                ("refresh_every", C.c_int32), ("warm_mode", C.c_int32), ("device", C.c_int32)]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(f) > t for f in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libcmpc.so in-tree for sm_100a with nvcc (cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the library (never builds implicitly on a GPU box: the .so travels in-tree)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CmpcError(-4, f"{LIB_PATH} is missing - run `python -c 'import __graft_entry__ as g; "
+                            f"g.build()'`; there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, f32p, u8p, i32p = C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p
+    L.cmpc_default_config.argtypes = [C.POINTER(Config), i32, i32]
+    L.cmpc_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.cmpc_destroy.argtypes = [vp]
+    L.cmpc_solve.argtypes = [vp, i32, i32, f32p, f32p, u8p, f32p, f32p, f32p, f32p, i32p, f32p,
+                             f32p, i32p, vp]
+    L.cmpc_solve_host.argtypes = [vp, i32, i32, f32p, f32p, u8p, f32p, f32p, f32p, f32p, i32p,
+                                  f32p, f32p, i32p]
+    L.cmpc_condense.argtypes = [vp, i32, f32p, f32p, u8p, f32p, f32p, f32p, vp]
+    L.cmpc_reset_warm.argtypes = [vp, u8p]
+    L.cmpc_get_warm.argtypes = [vp, i32, i32, f32p, f32p, vp]
+    L.cmpc_set_warm.argtypes = [vp, i32, i32, f32p, f32p, vp]
+    L.cmpc_launch_count.argtypes = [vp]
+    L.cmpc_launch_count.restype = C.c_int64
+    L.cmpc_supported_horizons.argtypes = [C.POINTER(C.c_int32), i32]
+    L.cmpc_version.restype = C.c_int
+    L.cmpc_last_error.restype = C.c_char_p
+    for name in SYMBOLS:
+        if name not in ("cmpc_launch_count", "cmpc_last_error"):
+            getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise CmpcError(rc, lib().cmpc_last_error().decode())
+
+
+def default_config(N: int, max_batch: int) -> Config:
+    cfg = Config()
+    check(lib().cmpc_default_config(C.byref(cfg), N, max_batch))
+    return cfg
+
+
+def supported_horizons():
+    buf = (C.c_int32 * 64)()
+    n = lib().cmpc_supported_horizons(buf, 64)
+    return [int(buf[i]) for i in range(min(n, 64))]

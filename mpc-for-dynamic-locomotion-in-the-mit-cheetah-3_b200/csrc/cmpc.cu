@@ -1,0 +1,501 @@
+// cmpc.cu - C ABI (include/cmpc.h) over the sm_100a kernels in cmpc_kernels.cuh.
+// No torch types, no CPU fallback: every entry point fails with CMPC_ERR_NO_DEVICE /
+// CMPC_ERR_CUDA when the CUDA device or the kernels are unavailable.
+#include "../../include/cmpc.h"
+#include "cmpc_kernels.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t e_ = (expr);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail(CMPC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                  \
+  } while (0)
+
+// ---- horizon Gram matrices (fp64 on the host, once per handle) -------------------------
+// M_a[j][j'] = 2 sum_{k>max(j,j')}^{N} ( w_pos,a dt^4 (k-1-j)(k-1-j') + w_vel,a dt^2 )
+// axes 0-2: Theta (rotated frame) with omega weights, axes 3-5: p with v weights.
+void axis_gram(int N, double dt, const float* w, std::vector<double>& M) {
+  M.assign((size_t)6 * N * N, 0.0);
+  for (int a = 0; a < 6; ++a) {
+    const double wp = w[a];                          // w[0:3] Theta, w[3:6] p
+    const double wv = w[6 + a];                      // w[6:9] omega, w[9:12] v
+    for (int j = 0; j < N; ++j)
+      for (int j2 = 0; j2 < N; ++j2) {
+        double acc = 0.0;
+        for (int k = (j > j2 ? j : j2) + 1; k <= N; ++k)
+          acc += wp * dt * dt * dt * dt * (double)(k - 1 - j) * (double)(k - 1 - j2) + wv * dt * dt;
+        M[((size_t)a * N + j) * N + j2] = 2.0 * acc;
+      }
+  }
+}
+
+struct Staging {
+  char* h_in = nullptr;    // pinned
+  char* h_out = nullptr;   // pinned
+  char* d_in = nullptr;
+  char* d_out = nullptr;
+  size_t in_bytes = 0, out_bytes = 0;
+  cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+  int cap = 0;             // problems
+};
+
+}  // namespace
+
+struct cmpc_handle {
+  cmpc_config cfg;
+  float* d_Minv = nullptr;
+  float* d_Mg = nullptr;
+  float* d_warm_x = nullptr;
+  float* d_warm_y = nullptr;
+  uint8_t* d_warm_valid = nullptr;
+  Staging st;
+  std::atomic<int64_t> launches{0};
+};
+
+namespace {
+
+using SolveLaunch = cudaError_t (*)(const cmpc::SolveParams&, cudaStream_t);
+using CondenseLaunch = cudaError_t (*)(const cmpc::CondenseParams&, cudaStream_t);
+
+template <int N, int SPLIT, int MINB>
+cudaError_t launch_solve(const cmpc::SolveParams& p, cudaStream_t s) {
+  cmpc::solve_kernel<N, SPLIT, MINB><<<p.B, cmpc::Geo<N, SPLIT>::THREADS, 0, s>>>(p);
+  return cudaGetLastError();
+}
+template <int N>
+cudaError_t launch_condense(const cmpc::CondenseParams& p, cudaStream_t s) {
+  cmpc::condense_kernel<N><<<p.B, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+struct HorizonEntry {
+  int N;
+  SolveLaunch solve;
+  CondenseLaunch condense;
+};
+
+// Horizons with compiled kernels.  <N, SPLIT, MINB>: SPLIT threads share one row of the
+// 6N x 6N wrench matrix so that the register-resident row slice stays <= 60 floats.
+const HorizonEntry kHorizons[] = {
+    {4, launch_solve<4, 1, 8>, launch_condense<4>},
+    {5, launch_solve<5, 1, 8>, launch_condense<5>},
+    {8, launch_solve<8, 1, 8>, launch_condense<8>},
+    {10, launch_solve<10, 1, 8>, launch_condense<10>},
+    {12, launch_solve<12, 2, 4>, launch_condense<12>},
+    {16, launch_solve<16, 2, 3>, launch_condense<16>},
+    {20, launch_solve<20, 2, 2>, launch_condense<20>},
+    {30, launch_solve<30, 4, 1>, launch_condense<30>},
+};
+
+const HorizonEntry* find_horizon(int N) {
+  for (const auto& e : kHorizons)
+    if (e.N == N) return &e;
+  return nullptr;
+}
+
+void fill_solve_params(const cmpc_handle* h, cmpc::SolveParams& p) {
+  const cmpc_config& c = h->cfg;
+  p.warm_x = h->d_warm_x;
+  p.warm_y = h->d_warm_y;
+  p.warm_valid = h->d_warm_valid;
+  p.Minv = h->d_Minv;
+  p.Mg = h->d_Mg;
+  p.dt = c.dt;
+  p.inv_mass = 1.0f / c.mass;
+  for (int i = 0; i < 3; ++i) p.ib[i] = c.ibody_inv[i];
+  for (int i = 0; i < 13; ++i) p.w[i] = c.w[i];
+  p.r_weight = c.r_weight;
+  p.f_min = c.f_min;
+  p.f_max = c.f_max;
+  p.rho = c.rho;
+  p.sigma = c.sigma;
+  p.alpha = c.alpha;
+  p.eps_abs = c.eps_abs;
+  p.eps_rel = c.eps_rel;
+  p.max_iter = c.max_iter;
+  p.check_every = c.check_every;
+  p.refresh_every = c.refresh_every;
+  p.warm_mode = c.warm_mode;
+}
+
+int check_batch(const cmpc_handle* h, int B, int slot0) {
+  if (!h) return fail(CMPC_ERR_INVALID, "null handle");
+  if (B < 0 || slot0 < 0 || (int64_t)slot0 + B > h->cfg.max_batch)
+    return fail(CMPC_ERR_INVALID, "batch [%d,%d) outside the handle's %d slots", slot0, slot0 + B,
+                h->cfg.max_batch);
+  return CMPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cmpc_version(void) { return CMPC_VERSION_MAJOR * 1000 + CMPC_VERSION_MINOR; }
+
+const char* cmpc_last_error(void) { return g_err.c_str(); }
+
+int cmpc_supported_horizons(int32_t* out, int32_t cap) {
+  int n = 0;
+  for (const auto& e : kHorizons) {
+    if (out && n < cap) out[n] = e.N;
+    ++n;
+  }
+  return n;
+}
+
+int cmpc_default_config(cmpc_config* cfg, int32_t N, int32_t max_batch) {
+  if (!cfg) return fail(CMPC_ERR_INVALID, "null config");
+  std::memset(cfg, 0, sizeof *cfg);
+  cfg->N = N;
+  cfg->max_batch = max_batch;
+  cfg->dt = 0.01f;                      // world.getTimeStep(), reference src/main.py:37
+  cfg->mass = 8.885f;                   // src/mpc.py:71
+  cfg->ibody_inv[0] = 1.0f / 0.24f;     // src/mpc.py:73-76
+  cfg->ibody_inv[1] = 1.0f;
+  cfg->ibody_inv[2] = 1.0f;
+  const float w[13] = {1e4f, 2.7e4f, 1e4f, 2.7e5f, 2.7e5f, 2.7e5f, 1e4f,
+                       1e4f, 1e4f, 1.6e4f, 1.6e4f, 1.6e4f, 0.f};   // src/mpc.py:121-134
+  std::memcpy(cfg->w, w, sizeof w);
+  cfg->r_weight = 0.0f;                 // src/mpc.py:121
+  cfg->f_min = 3.0f;                    // src/mpc.py:45-46
+  cfg->f_max = 100.0f;
+  cfg->rho = 0.3f;
+  cfg->sigma = 1e-6f;
+  cfg->alpha = 1.6f;
+  cfg->eps_abs = 1e-3f;                 // OSQP defaults (reference keeps them)
+  cfg->eps_rel = 1e-3f;
+  cfg->max_iter = 1000;                 // src/mpc.py:51
+  cfg->check_every = 5;
+  cfg->refresh_every = 25;
+  cfg->warm_mode = CMPC_WARM_PRIMAL;
+  cfg->device = 0;
+  return CMPC_OK;
+}
+
+int cmpc_create(const cmpc_config* cfg, cmpc_handle** out) {
+  if (!cfg || !out) return fail(CMPC_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const cmpc_config& c = *cfg;
+  if (!find_horizon(c.N))
+    return fail(CMPC_ERR_UNSUPPORTED, "horizon N=%d has no compiled kernel (see cmpc_supported_horizons)", c.N);
+  if (c.max_batch <= 0) return fail(CMPC_ERR_INVALID, "max_batch must be positive");
+  if (!(c.dt > 0) || !(c.mass > 0) || !(c.rho > 0) || !(c.sigma >= 0) || !(c.alpha > 0 && c.alpha < 2))
+    return fail(CMPC_ERR_INVALID, "dt, mass, rho must be > 0, sigma >= 0, 0 < alpha < 2");
+  if (!(c.f_min <= c.f_max)) return fail(CMPC_ERR_INVALID, "f_min > f_max");
+  if (c.max_iter < 0 || c.check_every <= 0 || c.refresh_every < 0)
+    return fail(CMPC_ERR_INVALID, "max_iter >= 0, check_every > 0, refresh_every >= 0 required");
+  if (c.warm_mode < 0 || c.warm_mode > 2) return fail(CMPC_ERR_INVALID, "bad warm_mode");
+  for (int i = 0; i < 12; ++i)
+    if (!(c.w[i] >= 0)) return fail(CMPC_ERR_INVALID, "state weights must be >= 0");
+  if (c.w[6] != c.w[7])
+    return fail(CMPC_ERR_UNSUPPORTED,
+                "the wrench-space form needs equal x/y angular-velocity weights (w[6]==w[7])");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(CMPC_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+  }
+  if (c.device < 0 || c.device >= ndev) return fail(CMPC_ERR_INVALID, "device %d of %d", c.device, ndev);
+  CUDA_TRY(cudaSetDevice(c.device));
+
+  const int N = c.N;
+  std::vector<double> M, Mi;
+  axis_gram(N, (double)c.dt, c.w, M);
+  Mi = M;
+  for (int a = 0; a < 6; ++a) {
+    // plain Gauss-Jordan with the textbook sign handling
+    double* A = Mi.data() + (size_t)a * N * N;
+    std::vector<double> aug((size_t)N * 2 * N, 0.0);
+    for (int i = 0; i < N; ++i) {
+      for (int j = 0; j < N; ++j) aug[(size_t)i * 2 * N + j] = A[i * N + j];
+      aug[(size_t)i * 2 * N + N + i] = 1.0;
+    }
+    for (int k = 0; k < N; ++k) {
+      const double piv = aug[(size_t)k * 2 * N + k];
+      if (!(piv > 0.0) || !std::isfinite(piv))
+        return fail(CMPC_ERR_INVALID, "horizon Gram matrix of axis %d is not positive definite "
+                                      "(position and velocity weight both zero?)", a);
+      for (int j = 0; j < 2 * N; ++j) aug[(size_t)k * 2 * N + j] /= piv;
+      for (int i = 0; i < N; ++i) {
+        if (i == k) continue;
+        const double f = aug[(size_t)i * 2 * N + k];
+        if (f == 0.0) continue;
+        for (int j = 0; j < 2 * N; ++j) aug[(size_t)i * 2 * N + j] -= f * aug[(size_t)k * 2 * N + j];
+      }
+    }
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) A[i * N + j] = aug[(size_t)i * 2 * N + N + j];
+  }
+  std::vector<float> Mf(M.size()), Mif(Mi.size());
+  for (size_t i = 0; i < M.size(); ++i) {
+    Mf[i] = (float)M[i];
+    Mif[i] = (float)Mi[i];
+  }
+
+  cmpc_handle* h = new cmpc_handle();
+  h->cfg = c;
+  const size_t mbytes = sizeof(float) * 6 * N * N;
+  const size_t slots = (size_t)c.max_batch;
+  cudaError_t e;
+  if ((e = cudaMalloc(&h->d_Minv, mbytes)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_Mg, mbytes)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_warm_x, slots * 12 * N * sizeof(float))) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_warm_y, slots * 20 * N * sizeof(float))) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_warm_valid, slots)) != cudaSuccess ||
+      (e = cudaMemcpy(h->d_Minv, Mif.data(), mbytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(h->d_Mg, Mf.data(), mbytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemset(h->d_warm_x, 0, slots * 12 * N * sizeof(float))) != cudaSuccess ||
+      (e = cudaMemset(h->d_warm_y, 0, slots * 20 * N * sizeof(float))) != cudaSuccess ||
+      (e = cudaMemset(h->d_warm_valid, 0, slots)) != cudaSuccess) {
+    cmpc_destroy(h);
+    return fail(CMPC_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return CMPC_OK;
+}
+
+int cmpc_destroy(cmpc_handle* h) {
+  if (!h) return CMPC_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaFree(h->d_Minv);
+  cudaFree(h->d_Mg);
+  cudaFree(h->d_warm_x);
+  cudaFree(h->d_warm_y);
+  cudaFree(h->d_warm_valid);
+  if (h->st.h_in) cudaFreeHost(h->st.h_in);
+  if (h->st.h_out) cudaFreeHost(h->st.h_out);
+  cudaFree(h->st.d_in);
+  cudaFree(h->st.d_out);
+  for (auto& s : h->st.streams)
+    if (s) cudaStreamDestroy(s);
+  delete h;
+  return CMPC_OK;
+}
+
+int64_t cmpc_launch_count(const cmpc_handle* h) { return h ? h->launches.load() : 0; }
+
+int cmpc_solve(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, const float* r,
+               const uint8_t* mask, const float* x_des, const float* mu, float* U, float* X,
+               int32_t* iters, float* pri_res, float* dua_res, int32_t* status, void* stream) {
+  int rc = check_batch(h, B, slot0);
+  if (rc) return rc;
+  if (B == 0) return CMPC_OK;
+  if (!x0 || !r || !mask || !x_des || !mu || !U) return fail(CMPC_ERR_INVALID, "null input/output pointer");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  cmpc::SolveParams p{};
+  fill_solve_params(h, p);
+  p.x0 = x0; p.r = r; p.mask = mask; p.x_des = x_des; p.mu = mu;
+  p.U = U; p.X = X; p.iters = iters; p.pri_res = pri_res; p.dua_res = dua_res; p.status = status;
+  p.B = B;
+  p.slot0 = slot0;
+  CUDA_TRY(find_horizon(h->cfg.N)->solve(p, (cudaStream_t)stream));
+  h->launches.fetch_add(1);
+  return CMPC_OK;
+}
+
+int cmpc_condense(cmpc_handle* h, int32_t B, const float* x0, const float* r, const uint8_t* mask,
+                  const float* x_des, float* H, float* g, void* stream) {
+  if (!h) return fail(CMPC_ERR_INVALID, "null handle");
+  if (B < 0) return fail(CMPC_ERR_INVALID, "negative batch");
+  if (B == 0) return CMPC_OK;
+  if (!x0 || !r || !mask || !x_des || !H || !g) return fail(CMPC_ERR_INVALID, "null pointer");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  cmpc::CondenseParams p{};
+  const cmpc_config& c = h->cfg;
+  p.x0 = x0; p.r = r; p.mask = mask; p.x_des = x_des; p.H = H; p.g = g; p.Mg = h->d_Mg;
+  p.B = B;
+  p.dt = c.dt;
+  p.inv_mass = 1.0f / c.mass;
+  for (int i = 0; i < 3; ++i) p.ib[i] = c.ibody_inv[i];
+  for (int i = 0; i < 13; ++i) p.w[i] = c.w[i];
+  p.r_weight = c.r_weight;
+  CUDA_TRY(find_horizon(c.N)->condense(p, (cudaStream_t)stream));
+  h->launches.fetch_add(1);
+  return CMPC_OK;
+}
+
+// ---- host-buffer path -------------------------------------------------------------------
+namespace {
+struct Layout {   // byte offsets of one chunk of C problems inside the in/out arenas
+  size_t x0, r, xdes, mu, mask, in_total;
+  size_t U, X, iters, pri, dua, status, out_total;
+};
+Layout make_layout(int N, int C, bool withX) {
+  Layout L{};
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  size_t o = 0;
+  L.x0 = o; o = al(o + (size_t)C * 13 * 4);
+  L.r = o; o = al(o + (size_t)C * 12 * N * 4);
+  L.xdes = o; o = al(o + (size_t)C * 13 * (N + 1) * 4);
+  L.mu = o; o = al(o + (size_t)C * 4);
+  L.mask = o; o = al(o + (size_t)C * N);
+  L.in_total = o;
+  o = 0;
+  L.U = o; o = al(o + (size_t)C * 12 * N * 4);
+  L.iters = o; o = al(o + (size_t)C * 4);
+  L.pri = o; o = al(o + (size_t)C * 4);
+  L.dua = o; o = al(o + (size_t)C * 4);
+  L.status = o; o = al(o + (size_t)C * 4);
+  L.X = o; if (withX) o = al(o + (size_t)C * 13 * (N + 1) * 4);
+  L.out_total = o;
+  return L;
+}
+}  // namespace
+
+int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, const float* r,
+                    const uint8_t* mask, const float* x_des, const float* mu, float* U, float* X,
+                    int32_t* iters, float* pri_res, float* dua_res, int32_t* status) {
+  int rc = check_batch(h, B, slot0);
+  if (rc) return rc;
+  if (B == 0) return CMPC_OK;
+  if (!x0 || !r || !mask || !x_des || !mu || !U) return fail(CMPC_ERR_INVALID, "null input/output pointer");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const int N = h->cfg.N;
+  Staging& st = h->st;
+  // chunking: overlap H2D(i+1) / solve(i) / D2H(i-1) on three streams
+  const int nchunk = B >= 2048 ? 4 : (B >= 512 ? 2 : 1);
+  const int C = (B + nchunk - 1) / nchunk;
+  const Layout L = make_layout(N, C, true);
+  if (st.cap < C || !st.h_in) {
+    if (st.h_in) cudaFreeHost(st.h_in);
+    if (st.h_out) cudaFreeHost(st.h_out);
+    cudaFree(st.d_in);
+    cudaFree(st.d_out);
+    st.h_in = st.h_out = st.d_in = st.d_out = nullptr;
+    st.cap = 0;
+    const size_t nb = 4;   // arenas per direction (>= nchunk)
+    CUDA_TRY(cudaMallocHost(&st.h_in, L.in_total * nb));
+    CUDA_TRY(cudaMallocHost(&st.h_out, L.out_total * nb));
+    CUDA_TRY(cudaMalloc(&st.d_in, L.in_total * nb));
+    CUDA_TRY(cudaMalloc(&st.d_out, L.out_total * nb));
+    st.in_bytes = L.in_total;
+    st.out_bytes = L.out_total;
+    st.cap = C;
+    for (auto& s : st.streams)
+      if (!s) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  }
+  const Layout La = make_layout(N, st.cap, true);   // arena strides use the allocated capacity
+  cmpc::SolveParams base{};
+  fill_solve_params(h, base);
+  const HorizonEntry* he = find_horizon(N);
+  for (int ci = 0; ci < nchunk; ++ci) {
+    const int lo = ci * C, n = (lo + C <= B ? C : B - lo);
+    if (n <= 0) break;
+    cudaStream_t s = st.streams[ci % 3];
+    char* hin = st.h_in + (size_t)ci * st.in_bytes;
+    char* din = st.d_in + (size_t)ci * st.in_bytes;
+    char* dout = st.d_out + (size_t)ci * st.out_bytes;
+    char* hout = st.h_out + (size_t)ci * st.out_bytes;
+    std::memcpy(hin + La.x0, x0 + (size_t)lo * 13, (size_t)n * 13 * 4);
+    std::memcpy(hin + La.r, r + (size_t)lo * 12 * N, (size_t)n * 12 * N * 4);
+    std::memcpy(hin + La.xdes, x_des + (size_t)lo * 13 * (N + 1), (size_t)n * 13 * (N + 1) * 4);
+    std::memcpy(hin + La.mu, mu + lo, (size_t)n * 4);
+    std::memcpy(hin + La.mask, mask + (size_t)lo * N, (size_t)n * N);
+    CUDA_TRY(cudaMemcpyAsync(din, hin, La.in_total, cudaMemcpyHostToDevice, s));
+    cmpc::SolveParams p = base;
+    p.x0 = (const float*)(din + La.x0);
+    p.r = (const float*)(din + La.r);
+    p.x_des = (const float*)(din + La.xdes);
+    p.mu = (const float*)(din + La.mu);
+    p.mask = (const uint8_t*)(din + La.mask);
+    p.U = (float*)(dout + La.U);
+    p.X = X ? (float*)(dout + La.X) : nullptr;
+    p.iters = (int32_t*)(dout + La.iters);
+    p.pri_res = (float*)(dout + La.pri);
+    p.dua_res = (float*)(dout + La.dua);
+    p.status = (int32_t*)(dout + La.status);
+    p.B = n;
+    p.slot0 = slot0 + lo;
+    CUDA_TRY(he->solve(p, s));
+    h->launches.fetch_add(1);
+    const size_t out_n = X ? La.out_total : La.X;
+    CUDA_TRY(cudaMemcpyAsync(hout, dout, out_n, cudaMemcpyDeviceToHost, s));
+  }
+  for (int ci = 0; ci < nchunk; ++ci) {
+    const int lo = ci * C, n = (lo + C <= B ? C : B - lo);
+    if (n <= 0) break;
+    CUDA_TRY(cudaStreamSynchronize(st.streams[ci % 3]));
+    const char* hout = st.h_out + (size_t)ci * st.out_bytes;
+    std::memcpy(U + (size_t)lo * 12 * N, hout + La.U, (size_t)n * 12 * N * 4);
+    if (X) std::memcpy(X + (size_t)lo * 13 * (N + 1), hout + La.X, (size_t)n * 13 * (N + 1) * 4);
+    if (iters) std::memcpy(iters + lo, hout + La.iters, (size_t)n * 4);
+    if (pri_res) std::memcpy(pri_res + lo, hout + La.pri, (size_t)n * 4);
+    if (dua_res) std::memcpy(dua_res + lo, hout + La.dua, (size_t)n * 4);
+    if (status) std::memcpy(status + lo, hout + La.status, (size_t)n * 4);
+  }
+  return CMPC_OK;
+}
+
+int cmpc_reset_warm(cmpc_handle* h, const uint8_t* slot_mask) {
+  if (!h) return fail(CMPC_ERR_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t slots = (size_t)h->cfg.max_batch;
+  if (!slot_mask) {
+    CUDA_TRY(cudaMemset(h->d_warm_valid, 0, slots));
+    return CMPC_OK;
+  }
+  std::vector<uint8_t> cur(slots);
+  CUDA_TRY(cudaMemcpy(cur.data(), h->d_warm_valid, slots, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < slots; ++i)
+    if (slot_mask[i]) cur[i] = 0;
+  CUDA_TRY(cudaMemcpy(h->d_warm_valid, cur.data(), slots, cudaMemcpyHostToDevice));
+  return CMPC_OK;
+}
+
+int cmpc_get_warm(cmpc_handle* h, int32_t B, int32_t slot0, float* x, float* y, void* stream) {
+  int rc = check_batch(h, B, slot0);
+  if (rc) return rc;
+  if (!x) return fail(CMPC_ERR_INVALID, "null pointer");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t N = (size_t)h->cfg.N;
+  CUDA_TRY(cudaMemcpyAsync(x, h->d_warm_x + (size_t)slot0 * 12 * N, (size_t)B * 12 * N * 4,
+                           cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (y)
+    CUDA_TRY(cudaMemcpyAsync(y, h->d_warm_y + (size_t)slot0 * 20 * N, (size_t)B * 20 * N * 4,
+                             cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return CMPC_OK;
+}
+
+int cmpc_set_warm(cmpc_handle* h, int32_t B, int32_t slot0, const float* x, const float* y,
+                  void* stream) {
+  int rc = check_batch(h, B, slot0);
+  if (rc) return rc;
+  if (!x) return fail(CMPC_ERR_INVALID, "null pointer");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t N = (size_t)h->cfg.N;
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemcpyAsync(h->d_warm_x + (size_t)slot0 * 12 * N, x, (size_t)B * 12 * N * 4,
+                           cudaMemcpyDeviceToDevice, s));
+  if (y)
+    CUDA_TRY(cudaMemcpyAsync(h->d_warm_y + (size_t)slot0 * 20 * N, y, (size_t)B * 20 * N * 4,
+                             cudaMemcpyDeviceToDevice, s));
+  else
+    CUDA_TRY(cudaMemsetAsync(h->d_warm_y + (size_t)slot0 * 20 * N, 0, (size_t)B * 20 * N * 4, s));
+  CUDA_TRY(cudaMemsetAsync(h->d_warm_valid + slot0, 1, (size_t)B, s));
+  return CMPC_OK;
+}
+
+}  // extern "C"

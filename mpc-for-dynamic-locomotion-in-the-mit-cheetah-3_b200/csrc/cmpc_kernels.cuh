@@ -1,0 +1,663 @@
+// cmpc_kernels.cuh - sm_100a device code of the batched convex-MPC solver.
+//
+// Problem (reference src/mpc.py:64-173): single-rigid-body dynamics linearised over N
+// stages, quadratic tracking cost on the 12 states, forces of swing legs pinned to zero,
+// fz in [f_min, f_max] and a friction pyramid |fx|,|fy| <= mu fz per stance leg.
+//
+// Formulation used on the GPU.  After eliminating the states the
+// cost depends on the forces u only through the 6N-vector of per-stage wrenches
+//     w = G u,   w_j = [ Rz I^-1 sum_l [r_jl]x f_jl ;  sum_l f_jl / m ]
+//     H = G' M G,  M = blockdiag over 6 axes of constant N x N Gram matrices (host, fp64).
+// OSQP-style ADMM needs K^-1 with K = H + sigma I + rho A'A; A'A is diagonal
+// (diag(2,2,1+4mu^2) per stance leg), so K = D + G' M G and by the matrix-inversion lemma
+//     K^-1 = D^-1 - D^-1 G' P^-1 G D^-1,    P = M^-1 + G D^-1 G'   (6N x 6N, SPD).
+// One CTA per problem:
+//   * "leg threads"   (4N): one per leg-stage, keep that leg's x(3), z(5), y(5) in registers;
+//   * "wrench threads"(6N*SPLIT): own one row (slice) of P, invert it in registers with a
+//     symmetric Gauss-Jordan sweep whose pivot rows are broadcast through shared memory,
+//     then apply P^-1 once per ADMM iteration.
+// The iteration is written in residual-correction form (K d = -r_dual - rho A' r_prim,
+// x += alpha d) so fp32 solve errors do not accumulate, and uses M G d = P^-1 s to keep the
+// wrench-space gradient v = M G x up to date without a second matrix-vector product.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cmpc {
+
+struct SolveParams {
+  const float* __restrict__ x0;
+  const float* __restrict__ r;
+  const uint8_t* __restrict__ mask;
+  const float* __restrict__ x_des;
+  const float* __restrict__ mu;
+  float* __restrict__ U;
+  float* __restrict__ X;
+  int32_t* __restrict__ iters;
+  float* __restrict__ pri_res;
+  float* __restrict__ dua_res;
+  int32_t* __restrict__ status;
+  float* __restrict__ warm_x;         // [slots][N][12]
+  float* __restrict__ warm_y;         // [slots][N][4][5]
+  uint8_t* __restrict__ warm_valid;   // [slots]
+  const float* __restrict__ Minv;     // [6][N][N]
+  const float* __restrict__ Mg;       // [6][N][N]
+  int32_t B;
+  int32_t slot0;
+  float dt, inv_mass;
+  float ib[3];
+  float w[13];
+  float r_weight, f_min, f_max, rho, sigma, alpha, eps_abs, eps_rel;
+  int32_t max_iter, check_every, refresh_every, warm_mode;
+};
+
+template <int N, int SPLIT>
+struct Geo {
+  static constexpr int NW = 6 * N;                                  // wrench dimension
+  static constexpr int NWP = ((NW + 4 * SPLIT - 1) / (4 * SPLIT)) * (4 * SPLIT);
+  static constexpr int COLS = NWP / SPLIT;                          // row slice per thread
+  static constexpr int NLEG = 4 * N;
+  static constexpr int ROWT = NW * SPLIT;                           // threads owning P rows
+  static constexpr int TMAX = ROWT > NLEG ? ROWT : NLEG;
+  static constexpr int THREADS = ((TMAX + 31) / 32) * 32;
+  static constexpr int WARPS = THREADS / 32;
+  static constexpr int NX = 13 * (N + 1);
+};
+
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+__device__ __forceinline__ float warp_max_nonneg(float v) {
+  // v >= 0 (or NaN): IEEE bit patterns of non-negative floats order like unsigned ints,
+  // NaN (0x7fc00000) sorts above every finite value so it propagates.
+  return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
+}
+
+// Per-leg geometry: Ghat = Rz * (Rz diag(ib) Rz') * [r]x   (torque rows of G, rotated frame)
+__device__ __forceinline__ void leg_map(float c, float s, const float ib[3], float rx, float ry,
+                                        float rz, float G[3][3]) {
+  // S = [r]x
+  const float S[3][3] = {{0.f, -rz, ry}, {rz, 0.f, -rx}, {-ry, rx, 0.f}};
+  float A[3][3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {   // A = diag(ib) * Rz' * S
+    A[0][k] = ib[0] * (c * S[0][k] + s * S[1][k]);
+    A[1][k] = ib[1] * (-s * S[0][k] + c * S[1][k]);
+    A[2][k] = ib[2] * S[2][k];
+  }
+  float T[3][3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {   // T = Rz * A  (= I_hat^-1 [r]x, reference src/mpc.py:78,103)
+    T[0][k] = c * A[0][k] - s * A[1][k];
+    T[1][k] = s * A[0][k] + c * A[1][k];
+    T[2][k] = A[2][k];
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {   // Ghat = Rz * T
+    G[0][k] = c * T[0][k] - s * T[1][k];
+    G[1][k] = s * T[0][k] + c * T[1][k];
+    G[2][k] = T[2][k];
+  }
+}
+
+// Linear term of the wrench-space cost: h[6j+a] = 2 sum_{k>j} (w_pos d^2 (k-1-j) e_pos + w_vel d e_vel)
+// with e = free response - x_des (angular velocity error rotated by Rz).
+template <int N>
+__device__ __forceinline__ float wrench_linear_term(int j, int a, const float* sx0,
+                                                    const float* sxd, float c, float s,
+                                                    const float* w, float dt) {
+  const float g = sx0[12];
+  const float rw0x = c * sx0[6] - s * sx0[7];
+  const float rw0y = s * sx0[6] + c * sx0[7];
+  const float rw0z = sx0[8];
+  float acc = 0.f;
+  for (int k = j + 1; k <= N; ++k) {
+    const float* xd = sxd + 13 * k;
+    const float kf = (float)k;
+    float e_pos, e_vel, wp, wv;
+    if (a < 3) {
+      const float rw0 = a == 0 ? rw0x : (a == 1 ? rw0y : rw0z);
+      const float rwd = a == 0 ? (c * xd[6] - s * xd[7]) : (a == 1 ? (s * xd[6] + c * xd[7]) : xd[8]);
+      e_pos = sx0[a] + kf * dt * rw0 - xd[a];
+      e_vel = rw0 - rwd;
+      wp = w[a];
+      wv = w[6 + a];
+    } else {
+      const int aa = a - 3;
+      float pf = sx0[3 + aa] + kf * dt * sx0[9 + aa];
+      float vf = sx0[9 + aa];
+      if (aa == 2) {
+        pf += 0.5f * kf * (kf - 1.f) * dt * dt * g;
+        vf += kf * dt * g;
+      }
+      e_pos = pf - xd[3 + aa];
+      e_vel = vf - xd[9 + aa];
+      wp = w[3 + aa];
+      wv = w[9 + aa];
+    }
+    acc += 2.f * (wp * dt * dt * (float)(k - 1 - j) * e_pos + wv * dt * e_vel);
+  }
+  return acc;
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused condense + factor + ADMM kernel.  One CTA per problem.
+// ---------------------------------------------------------------------------------------
+template <int N, int SPLIT, int MINB>
+__global__ void __launch_bounds__(Geo<N, SPLIT>::THREADS, MINB)
+solve_kernel(const SolveParams p) {
+  using G_ = Geo<N, SPLIT>;
+  constexpr int NW = G_::NW, NWP = G_::NWP, COLS = G_::COLS, NLEG = G_::NLEG;
+  constexpr int THREADS = G_::THREADS, WARPS = G_::WARPS, NX = G_::NX;
+
+  __shared__ __align__(16) float s_x0[16];
+  __shared__ __align__(16) float s_xd[NX + 3];
+  __shared__ __align__(16) float s_G[NLEG][12];        // Ghat (9) + dxy, dz, pad per leg
+  __shared__ __align__(16) float s_row[2][NWP + 4];    // pivot-row double buffer (+ 1/pivot)
+  __shared__ __align__(16) float s_s[NWP];             // wrench-space rhs  s = G D^-1 b
+  __shared__ __align__(16) float s_q[NWP];             // q = P^-1 s   (also: w, v scratch)
+  __shared__ __align__(16) float s_h[NWP];             // linear term h
+  __shared__ float s_red[2][WARPS][8];
+  __shared__ int s_mask[N];
+
+  const int b = blockIdx.x;
+  if (b >= p.B) return;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int slot = p.slot0 + b;
+
+  // ---- phase 0: stage the per-problem record (coalesced 4-byte loads) -------------------
+  for (int i = tid; i < 13; i += THREADS) s_x0[i] = __ldg(p.x0 + (size_t)b * 13 + i);
+  for (int i = tid; i < NX; i += THREADS) s_xd[i] = __ldg(p.x_des + (size_t)b * NX + i);
+  for (int i = tid; i < N; i += THREADS) s_mask[i] = (int)__ldg(p.mask + (size_t)b * N + i);
+  for (int i = tid; i < NWP; i += THREADS) { s_s[i] = 0.f; s_q[i] = 0.f; s_h[i] = 0.f; }
+  const float mu = __ldg(p.mu + b);
+  __syncthreads();
+
+  float sn, cs;
+  sincosf(s_x0[2], &sn, &cs);
+  const float im = p.inv_mass;
+  const float rho = p.rho, alpha = p.alpha;
+  const float rho_inv = 1.f / rho;
+
+  // ---- phase 1: leg geometry, linear term -----------------------------------------------
+  const bool is_leg = tid < NLEG;
+  const int lj = tid >> 2, ll = tid & 3;            // stage, leg of a leg thread
+  bool stance = false;
+  float Gh[3][3];
+  float dxy = 0.f, dz = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Gh[a][k] = 0.f;
+  if (is_leg) {
+    stance = (s_mask[lj] >> ll) & 1;
+    const float* rp = p.r + ((size_t)b * NLEG + tid) * 3;
+    const float rx = __ldg(rp), ry = __ldg(rp + 1), rz = __ldg(rp + 2);
+    leg_map(cs, sn, p.ib, rx, ry, rz, Gh);
+    if (stance) {
+      dxy = 1.f / (p.sigma + 2.f * p.r_weight + 2.f * rho);
+      dz = 1.f / (p.sigma + 2.f * p.r_weight + rho * (1.f + 4.f * mu * mu));
+    } else {
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Gh[a][k] = 0.f;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) s_G[tid][3 * a + k] = Gh[a][k];
+    s_G[tid][9] = dxy;
+    s_G[tid][10] = dz;
+    s_G[tid][11] = stance ? 1.f : 0.f;
+  }
+  const bool is_row = tid < G_::ROWT;
+  const int ri = tid / SPLIT, rs = tid % SPLIT;      // P row, slice
+  const int rj = ri / 6, ra = ri % 6;                // stage, axis of that row
+  if (is_row && rs == 0) s_h[ri] = wrench_linear_term<N>(rj, ra, s_x0, s_xd, cs, sn, p.w, p.dt);
+  __syncthreads();
+
+  // ---- phase 2: P = M^-1 + E (row slices in registers) ------------------------------------
+  float row[COLS];
+#pragma unroll
+  for (int c = 0; c < COLS; ++c) row[c] = 0.f;
+  if (is_row) {
+    // E_j[ra][a'] = sum_l sum_c Gp[ra][c] d_c Gp[a'][c],  Gp = [Ghat ; I/m]
+    float E[6];
+#pragma unroll
+    for (int a2 = 0; a2 < 6; ++a2) E[a2] = 0.f;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const float* g = s_G[4 * rj + l];
+      const float d[3] = {g[9], g[9], g[10]};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float mine = (ra < 3 ? g[3 * ra + c] : (ra - 3 == c ? im : 0.f)) * d[c];
+#pragma unroll
+        for (int a2 = 0; a2 < 3; ++a2) E[a2] += mine * g[3 * a2 + c];
+        E[3 + c] += mine * im;
+      }
+    }
+    const float* mi = p.Minv + ((size_t)ra * N + rj) * N;
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      const int col = rs * COLS + c;
+      const int j2 = col / 6, a2 = col % 6;
+      float v = 0.f;
+      if (col < NW) {
+        if (a2 == ra) v = __ldg(mi + j2);
+        if (j2 == rj) v += E[a2];
+      }
+      row[c] = v;
+    }
+  }
+
+  // ---- phase 3: symmetric Gauss-Jordan sweep, rows in registers -> row = -P^-1 ------------
+  for (int k = 0; k < NW; ++k) {
+    float* buf = s_row[k & 1];
+    if (is_row && ri == k) {
+#pragma unroll
+      for (int c = 0; c < COLS; c += 4)
+        *reinterpret_cast<float4*>(buf + rs * COLS + c) =
+            make_float4(row[c], row[c + 1], row[c + 2], row[c + 3]);
+      if (k / COLS == rs) {   // this slice holds the pivot: publish 1/pivot, patch entry k
+        const float akk = buf[k];
+        buf[k] = akk - 1.f;
+        buf[NWP] = 1.f / akk;
+      }
+    }
+    __syncthreads();
+    if (is_row) {
+      const float d = buf[NWP];
+      const float* pr = buf + rs * COLS;
+      if (ri == k) {
+        const float nf = 1.f + d;     // row = -row + (1+d) p'
+#pragma unroll
+        for (int c = 0; c < COLS; c += 4) {
+          const float4 pv = *reinterpret_cast<const float4*>(pr + c);
+          row[c] = fmaf(nf, pv.x, -row[c]);
+          row[c + 1] = fmaf(nf, pv.y, -row[c + 1]);
+          row[c + 2] = fmaf(nf, pv.z, -row[c + 2]);
+          row[c + 3] = fmaf(nf, pv.w, -row[c + 3]);
+        }
+      } else {
+        const float nf = -buf[ri] * d;  // row -= (a_ik d) p'
+#pragma unroll
+        for (int c = 0; c < COLS; c += 4) {
+          const float4 pv = *reinterpret_cast<const float4*>(pr + c);
+          row[c] = fmaf(nf, pv.x, row[c]);
+          row[c + 1] = fmaf(nf, pv.y, row[c + 1]);
+          row[c + 2] = fmaf(nf, pv.z, row[c + 2]);
+          row[c + 3] = fmaf(nf, pv.w, row[c + 3]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 4: initial iterate -----------------------------------------------------------
+  float x[3] = {0.f, 0.f, 0.f};
+  float y[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float z[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float gl[3] = {0.f, 0.f, 0.f};          // linear term of this leg:  G' h
+  float vj[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // wrench-space gradient v = M G x of this stage
+  const bool warm = p.warm_mode != 0 && p.warm_valid[slot] != 0;
+  if (is_leg && stance) {
+    const float* hj = s_h + 6 * lj;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      gl[k] = Gh[0][k] * hj[0] + Gh[1][k] * hj[1] + Gh[2][k] * hj[2] + im * hj[3 + k];
+    if (warm) {
+      const float* wx = p.warm_x + ((size_t)slot * NLEG + tid) * 3;
+      x[0] = wx[0]; x[1] = wx[1]; x[2] = wx[2];
+      if (p.warm_mode == 2) {
+        const float* wy = p.warm_y + ((size_t)slot * NLEG + tid) * 5;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) y[k] = wy[k];
+      }
+    }
+    z[0] = fminf(fmaxf(x[2], p.f_min), p.f_max);
+    z[1] = fminf(x[0] - mu * x[2], 0.f);
+    z[2] = fminf(-x[0] - mu * x[2], 0.f);
+    z[3] = fminf(x[1] - mu * x[2], 0.f);
+    z[4] = fminf(-x[1] - mu * x[2], 0.f);
+  }
+
+  // exact wrench-space gradient  v = M (G x)  (uniform: every thread takes part)
+  auto refresh_gradient = [&]() {
+    if (is_leg) {
+      float wv[6];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        wv[a] = quad_sum(Gh[a][0] * x[0] + Gh[a][1] * x[1] + Gh[a][2] * x[2]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) wv[3 + k] = quad_sum(x[k] * im);
+      if (ll < 3) *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = make_float2(wv[2 * ll], wv[2 * ll + 1]);
+    }
+    __syncthreads();
+    if (is_row && rs == 0) {
+      const float* mg = p.Mg + ((size_t)ra * N + rj) * N;
+      float acc = 0.f;
+#pragma unroll
+      for (int j2 = 0; j2 < N; ++j2) acc = fmaf(__ldg(mg + j2), s_s[6 * j2 + ra], acc);
+      s_q[ri] = acc;
+    }
+    __syncthreads();
+    if (is_leg) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) vj[a] = s_q[6 * lj + a];
+    }
+    __syncthreads();
+  };
+  if (warm) refresh_gradient();
+
+  // constant part of the dual tolerance: ||G' h||_inf
+  float ng = 0.f;
+  {
+    float m = fmaxf(fabsf(gl[0]), fmaxf(fabsf(gl[1]), fabsf(gl[2])));
+    m = warp_max_nonneg(m);
+    if (lane == 0) s_red[1][warp][0] = m;
+    __syncthreads();
+#pragma unroll
+    for (int wv = 0; wv < WARPS; ++wv) ng = fmaxf(ng, s_red[1][wv][0]);
+    __syncthreads();
+  }
+
+  // ---- phase 5: ADMM ------------------------------------------------------------------------
+  int it = 0;
+  int status = 0;
+  float pri = 0.f, dua = 0.f;
+  const float two_rw = 2.f * p.r_weight;
+  for (;;) {
+    if (p.refresh_every > 0 && it > 0 && (it % p.refresh_every) == 0) refresh_gradient();
+    // leg phase A: residuals of the current iterate, rhs of the correction equation
+    float t[3] = {0.f, 0.f, 0.f};
+    const bool chk = (it % p.check_every) == 0 || it >= p.max_iter;
+    float st_[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (is_leg) {
+      float Ax[5], Aty[3], Hx[3], rd[3], rp[5];
+      Ax[0] = x[2];
+      Ax[1] = x[0] - mu * x[2];
+      Ax[2] = -x[0] - mu * x[2];
+      Ax[3] = x[1] - mu * x[2];
+      Ax[4] = -x[1] - mu * x[2];
+      Aty[0] = y[1] - y[2];
+      Aty[1] = y[3] - y[4];
+      Aty[2] = y[0] - mu * (y[1] + y[2] + y[3] + y[4]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        Hx[k] = Gh[0][k] * vj[0] + Gh[1][k] * vj[1] + Gh[2][k] * vj[2] + im * vj[3 + k] + two_rw * x[k];
+        rd[k] = Hx[k] + gl[k] + Aty[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) rp[k] = Ax[k] - z[k];
+      if (!stance) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { Hx[k] = 0.f; rd[k] = 0.f; }
+      }
+      // b = -rd - rho A' rp ; t = D^-1 b
+      const float b0 = -rd[0] - rho * (rp[1] - rp[2]);
+      const float b1 = -rd[1] - rho * (rp[3] - rp[4]);
+      const float b2 = -rd[2] - rho * (rp[0] - mu * (rp[1] + rp[2] + rp[3] + rp[4]));
+      t[0] = dxy * b0;
+      t[1] = dxy * b1;
+      t[2] = dz * b2;
+      float sv[6];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        sv[a] = quad_sum(Gh[a][0] * t[0] + Gh[a][1] * t[1] + Gh[a][2] * t[2]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) sv[3 + k] = quad_sum(t[k] * im);
+      if (ll < 3) *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = make_float2(sv[2 * ll], sv[2 * ll + 1]);
+      if (chk) {
+        float m;
+        m = 0.f;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) m = fmaxf(m, fabsf(rp[k]));
+        st_[0] = m;                                            // primal residual
+        st_[1] = fmaxf(fabsf(rd[0]), fmaxf(fabsf(rd[1]), fabsf(rd[2])));   // dual residual
+        m = 0.f;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) m = fmaxf(m, fmaxf(fabsf(Ax[k]), fabsf(z[k])));
+        st_[2] = m;                                            // max(|Ax|,|z|)
+        m = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) m = fmaxf(m, fmaxf(fabsf(Hx[k]), fabsf(Aty[k])));
+        st_[3] = m;                                            // max(|Hx|,|A'y|)
+        // NaN guard: a NaN anywhere makes the sum NaN
+        st_[4] = fabsf((x[0] + x[1] + x[2]) * 0.f);
+      }
+    }
+    if (chk) {
+      const int pb = (it / p.check_every) & 1;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const float m = warp_max_nonneg(st_[k]);
+        if (lane == 0) s_red[pb][warp][k] = m;
+      }
+    }
+    __syncthreads();
+    if (chk) {
+      const int pb = (it / p.check_every) & 1;
+      float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, m4 = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < WARPS; ++wv) {
+        m0 = fmaxf(m0, s_red[pb][wv][0]);
+        m1 = fmaxf(m1, s_red[pb][wv][1]);
+        m2 = fmaxf(m2, s_red[pb][wv][2]);
+        m3 = fmaxf(m3, s_red[pb][wv][3]);
+        m4 += s_red[pb][wv][4];
+      }
+      pri = m0;
+      dua = m1;
+      const float eps_p = p.eps_abs + p.eps_rel * m2;
+      const float eps_d = p.eps_abs + p.eps_rel * fmaxf(m3, ng);
+      if (!(m4 == 0.f) || !(m0 == m0) || !(m1 == m1)) { status = -1; break; }
+      if (pri <= eps_p && dua <= eps_d) { status = 1; break; }
+      if (it >= p.max_iter) { status = 0; break; }
+    }
+    // wrench phase: q = P^-1 s   (row holds -P^-1)
+    if (is_row) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const float* sp = s_s + rs * COLS;
+#pragma unroll
+      for (int c = 0; c < COLS; c += 4) {
+        const float4 sv4 = *reinterpret_cast<const float4*>(sp + c);
+        a0 = fmaf(row[c], sv4.x, a0);
+        a1 = fmaf(row[c + 1], sv4.y, a1);
+        a2 = fmaf(row[c + 2], sv4.z, a2);
+        a3 = fmaf(row[c + 3], sv4.w, a3);
+      }
+      float acc = (a0 + a1) + (a2 + a3);
+      if (SPLIT >= 2) acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (SPLIT >= 4) acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (rs == 0) s_q[ri] = -acc;
+    } else if (SPLIT >= 2) {
+      // keep whole warps converged for the shuffles above
+      float acc = 0.f;
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (SPLIT >= 4) acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    }
+    __syncthreads();
+    // leg phase B: x += alpha d, relaxed projection, dual update
+    if (is_leg && stance) {
+      const float* q = s_q + 6 * lj;
+      float qv[6];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) qv[a] = q[a];
+      float d[3];
+      d[0] = t[0] - dxy * (Gh[0][0] * qv[0] + Gh[1][0] * qv[1] + Gh[2][0] * qv[2] + im * qv[3]);
+      d[1] = t[1] - dxy * (Gh[0][1] * qv[0] + Gh[1][1] * qv[1] + Gh[2][1] * qv[2] + im * qv[4]);
+      d[2] = t[2] - dz * (Gh[0][2] * qv[0] + Gh[1][2] * qv[1] + Gh[2][2] * qv[2] + im * qv[5]);
+#pragma unroll
+      for (int a = 0; a < 6; ++a) vj[a] = fmaf(alpha, qv[a], vj[a]);
+      const float xt0 = x[0] + d[0], xt1 = x[1] + d[1], xt2 = x[2] + d[2];
+      float zt[5];
+      zt[0] = xt2;
+      zt[1] = xt0 - mu * xt2;
+      zt[2] = -xt0 - mu * xt2;
+      zt[3] = xt1 - mu * xt2;
+      zt[4] = -xt1 - mu * xt2;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) x[k] = fmaf(alpha, d[k], x[k]);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const float zh = alpha * zt[k] + (1.f - alpha) * z[k];
+        float zn = zh + y[k] * rho_inv;
+        zn = (k == 0) ? fminf(fmaxf(zn, p.f_min), p.f_max) : fminf(zn, 0.f);
+        y[k] = fmaf(rho, zh - zn, y[k]);
+        z[k] = zn;
+      }
+    }
+    ++it;
+  }
+
+  // ---- phase 6: outputs -----------------------------------------------------------------------
+  if (is_leg) {
+    float* up = p.U + ((size_t)b * NLEG + tid) * 3;
+    up[0] = x[0]; up[1] = x[1]; up[2] = x[2];
+    float* wx = p.warm_x + ((size_t)slot * NLEG + tid) * 3;
+    wx[0] = x[0]; wx[1] = x[1]; wx[2] = x[2];
+    float* wy = p.warm_y + ((size_t)slot * NLEG + tid) * 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) wy[k] = y[k];
+  }
+  if (tid == 0) {
+    if (p.iters) p.iters[b] = it;
+    if (p.pri_res) p.pri_res[b] = pri;
+    if (p.dua_res) p.dua_res[b] = dua;
+    if (p.status) p.status[b] = status;
+    p.warm_valid[slot] = status >= 0 ? 1 : 0;
+  }
+  if (p.X) {
+    // predicted states X = free response + forced response of the wrench sequence w = G x
+    __syncthreads();
+    if (is_leg) {
+      float wv[6];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        wv[a] = quad_sum(Gh[a][0] * x[0] + Gh[a][1] * x[1] + Gh[a][2] * x[2]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) wv[3 + k] = quad_sum(x[k] * im);
+      if (ll < 3) *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = make_float2(wv[2 * ll], wv[2 * ll + 1]);
+    }
+    __syncthreads();
+    const float dt = p.dt, g = s_x0[12];
+    for (int o = tid; o < NX; o += THREADS) {
+      const int k = o / 13, cidx = o % 13;
+      const float kf = (float)k;
+      float val;
+      if (cidx == 12) {
+        val = g;
+      } else if (cidx < 3) {           // Theta_k = Theta_0 + k d Rz w0 + d^2 sum (k-1-j) tau^_j
+        const float rw0 = cidx == 0 ? (cs * s_x0[6] - sn * s_x0[7])
+                                    : (cidx == 1 ? (sn * s_x0[6] + cs * s_x0[7]) : s_x0[8]);
+        float acc = 0.f;
+        for (int j = 0; j < k; ++j) acc += (float)(k - 1 - j) * s_s[6 * j + cidx];
+        val = s_x0[cidx] + kf * dt * rw0 + dt * dt * acc;
+      } else if (cidx < 6) {           // p_k
+        const int aa = cidx - 3;
+        float acc = 0.f;
+        for (int j = 0; j < k; ++j) acc += (float)(k - 1 - j) * s_s[6 * j + 3 + aa];
+        val = s_x0[cidx] + kf * dt * s_x0[9 + aa] + dt * dt * acc;
+        if (aa == 2) val += 0.5f * kf * (kf - 1.f) * dt * dt * g;
+      } else if (cidx < 9) {           // omega_k = omega_0 + d Rz' sum tau^_j
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        for (int j = 0; j < k; ++j) { sx += s_s[6 * j]; sy += s_s[6 * j + 1]; sz += s_s[6 * j + 2]; }
+        const int aa = cidx - 6;
+        const float rot = aa == 0 ? (cs * sx + sn * sy) : (aa == 1 ? (-sn * sx + cs * sy) : sz);
+        val = s_x0[cidx] + dt * rot;
+      } else {                         // v_k
+        const int aa = cidx - 9;
+        float acc = 0.f;
+        for (int j = 0; j < k; ++j) acc += s_s[6 * j + 3 + aa];
+        val = s_x0[cidx] + dt * acc;
+        if (aa == 2) val += kf * dt * g;
+      }
+      p.X[(size_t)b * NX + o] = val;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Dense condensed QP export: H [B,12N,12N], g [B,12N]  (parity / inspection path)
+// grid = (B), block = 256
+// ---------------------------------------------------------------------------------------
+struct CondenseParams {
+  const float* __restrict__ x0;
+  const float* __restrict__ r;
+  const uint8_t* __restrict__ mask;
+  const float* __restrict__ x_des;
+  float* __restrict__ H;
+  float* __restrict__ g;
+  const float* __restrict__ Mg;   // [6][N][N]
+  int32_t B;
+  float dt, inv_mass;
+  float ib[3];
+  float w[13];
+  float r_weight;
+};
+
+template <int N>
+__global__ void __launch_bounds__(256) condense_kernel(const CondenseParams p) {
+  constexpr int NLEG = 4 * N, NU = 12 * N, NX = 13 * (N + 1), NW = 6 * N;
+  __shared__ float s_x0[16];
+  __shared__ float s_xd[NX];
+  __shared__ float s_Gp[NLEG][3][6];     // Gp' : per leg, per force component c, the 6 wrench rows
+  __shared__ float s_h[NW];
+  __shared__ float s_M[6][N][N];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (b >= p.B) return;
+  for (int i = tid; i < 13; i += 256) s_x0[i] = __ldg(p.x0 + (size_t)b * 13 + i);
+  for (int i = tid; i < NX; i += 256) s_xd[i] = __ldg(p.x_des + (size_t)b * NX + i);
+  for (int i = tid; i < 6 * N * N; i += 256) (&s_M[0][0][0])[i] = __ldg(p.Mg + i);
+  __syncthreads();
+  float sn, cs;
+  sincosf(s_x0[2], &sn, &cs);
+  for (int t = tid; t < NLEG; t += 256) {
+    const int j = t >> 2, l = t & 3;
+    const bool stance = (__ldg(p.mask + (size_t)b * N + j) >> l) & 1;
+    const float* rp = p.r + ((size_t)b * NLEG + t) * 3;
+    float Gh[3][3];
+    leg_map(cs, sn, p.ib, __ldg(rp), __ldg(rp + 1), __ldg(rp + 2), Gh);
+    for (int c = 0; c < 3; ++c) {
+      for (int a = 0; a < 3; ++a) s_Gp[t][c][a] = stance ? Gh[a][c] : 0.f;
+      for (int a = 0; a < 3; ++a) s_Gp[t][c][3 + a] = (stance && a == c) ? p.inv_mass : 0.f;
+    }
+  }
+  for (int i = tid; i < NW; i += 256)
+    s_h[i] = wrench_linear_term<N>(i / 6, i % 6, s_x0, s_xd, cs, sn, p.w, p.dt);
+  __syncthreads();
+  // g = G' h
+  for (int u = tid; u < NU; u += 256) {
+    const int t = u / 3, c = u % 3, j = t >> 2;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) acc += s_Gp[t][c][a] * s_h[6 * j + a];
+    p.g[(size_t)b * NU + u] = acc;
+  }
+  // H = G' M G  (+ 2 r_weight on the diagonal of stance forces); float4 stores along rows
+  float* Hb = p.H + (size_t)b * NU * NU;
+  for (int e = tid; e < NU * (NU / 4); e += 256) {
+    const int row = e / (NU / 4), c4 = (e % (NU / 4)) * 4;
+    const int t1 = row / 3, c1 = row % 3, j1 = t1 >> 2;
+    float out[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int col = c4 + q;
+      const int t2 = col / 3, c2 = col % 3, j2 = t2 >> 2;
+      float acc = 0.f;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) acc += s_Gp[t1][c1][a] * s_M[a][j1][j2] * s_Gp[t2][c2][a];
+      if (row == col && s_Gp[t1][c1][3 + c1] != 0.f) acc += 2.f * p.r_weight;
+      out[q] = acc;
+    }
+    *reinterpret_cast<float4*>(Hb + (size_t)row * NU + c4) = make_float4(out[0], out[1], out[2], out[3]);
+  }
+}
+
+}  // namespace cmpc

@@ -1,0 +1,298 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI
+(ctypes -> libcmpc.so), against the fp64 oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): forces within 1e-3 relative / 1e-2 N absolute,
+written as |a-b| <= 1e-2 + 1e-3 |b|.  Because the reference's QP has zero force weight
+(src/mpc.py:121) its optimal force split over the legs is not unique,
+so full force vectors are compared (a) iterate-for-iterate against the same ADMM in fp64
+and (b) against the tight fp64 optimum when a force weight makes the optimum unique;
+with the reference's r_weight = 0 the tight comparison is on the unique quantities
+(state trajectory, objective, per-stage net wrench)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import mpc_b200 as pkg                                   # noqa: E402
+from mpc_b200.problems import synthetic_batch, DT, GAIT_NAMES   # noqa: E402
+from oracle import condensed_admm as ca, srbd_qp          # noqa: E402
+
+ATOL, RTOL = 1e-2, 1e-3
+
+
+def close(a, b, atol=ATOL, rtol=RTOL):
+    return np.all(np.abs(a - b) <= atol + rtol * np.abs(b))
+
+
+def dev_args(pb, dev="cuda:0"):
+    return [torch.from_numpy(a).to(dev) for a in pb.f32()]
+
+
+def gpu_solve(pb, want_X=True, **opts):
+    mpc = pkg.BatchedMPC(N=pb.N, max_batch=pb.B, **opts)
+    U, X, st = mpc.solve(*dev_args(pb), want_X=want_X)
+    torch.cuda.synchronize()
+    out = dict(U=U.cpu().numpy().astype(np.float64),
+               X=None if X is None else X.cpu().numpy().astype(np.float64),
+               iters=st.iters.cpu().numpy(), pri=st.pri_res.cpu().numpy(),
+               dua=st.dua_res.cpu().numpy(), status=st.status.cpu().numpy(), mpc=mpc)
+    return out
+
+
+def oracle_fixed(pb, b, K, mpc, **kw):
+    x0, r, stance, xd, mu = pb.problem(b)
+    return ca.solve_problem(x0, r, stance, xd, mu, DT, fixed_iters=K, rho=float(mpc.cfg.rho),
+                            sigma=float(mpc.cfg.sigma), alpha=float(mpc.cfg.alpha), **kw)
+
+
+# ------------------------------------------------------------------------------------------
+def test_library_loaded_and_device():
+    assert torch.cuda.is_available()
+    assert pkg._capi.lib().cmpc_version() >= 1
+    assert 10 in pkg._capi.supported_horizons()
+
+
+@pytest.mark.parametrize("N,gaits", [(10, ("trot",)), (10, GAIT_NAMES), (5, ("trot",)),
+                                     (20, ("pseudo_gallop",)), (30, ("trot",))])
+def test_condense_matches_oracle(N, gaits):
+    """H, g of cmpc_condense vs the plain recursion of reference src/mpc.py:64-136."""
+    pb = synthetic_batch(6, N=N, gaits=gaits, seed=11)
+    mpc = pkg.BatchedMPC(N=N, max_batch=pb.B)
+    x0, r, mask, xd, mu = dev_args(pb)
+    H, g = mpc.condense(x0, r, mask, xd)
+    torch.cuda.synchronize()
+    H, g = H.cpu().numpy().astype(np.float64), g.cpu().numpy().astype(np.float64)
+    for b in range(pb.B):
+        px0, pr, pst, pxd, _ = pb.problem(b)
+        # the kernel sees fp32 inputs: give the oracle the same rounded inputs
+        px0, pr, pxd = (np.float32(px0).astype(np.float64), np.float32(pr).astype(np.float64),
+                        np.float32(pxd).astype(np.float64))
+        Ho, go, _, _, idx = srbd_qp.condensed_qp(px0, pr, pst, pxd, DT)
+        sel = np.array([12 * i + 3 * l + k for (i, l) in idx for k in range(3)], dtype=int)
+        scale = max(np.abs(Ho).max(), 1e-12)
+        assert np.abs(H[b][np.ix_(sel, sel)] - Ho).max() <= 2e-5 * scale
+        assert np.abs(g[b][sel] - go).max() <= 2e-4 * max(np.abs(go).max(), 1.0)
+        off = np.setdiff1d(np.arange(12 * N), sel)
+        assert np.all(H[b][off, :] == 0) and np.all(H[b][:, off] == 0) and np.all(g[b][off] == 0)
+
+
+@pytest.mark.parametrize("N,gaits,B,K", [(10, ("trot",), 32, 40), (10, GAIT_NAMES, 32, 60),
+                                         (5, ("trot",), 8, 40), (8, ("amble",), 8, 40),
+                                         (12, ("trot",), 6, 40), (16, ("pronk",), 6, 40),
+                                         (20, ("pseudo_gallop",), 6, 40), (30, ("trot",), 6, 40)])
+def test_iterate_parity_fixed_iterations(N, gaits, B, K):
+    """Same ADMM, same iteration count: fp32 CUDA vs fp64 oracle, full force vector."""
+    pb = synthetic_batch(B, N=N, gaits=gaits, seed=5)
+    out = gpu_solve(pb, max_iter=K, check_every=100000, eps_abs=0.0, eps_rel=0.0, warm_mode=0)
+    assert np.all(out["iters"] == K) and np.all(out["status"] == 0)
+    worst = 0.0
+    for b in range(B):
+        ref = oracle_fixed(pb, b, K, out["mpc"])
+        worst = max(worst, np.abs(out["U"][b] - ref["U"]).max())
+        assert close(out["U"][b], ref["U"]), (b, np.abs(out["U"][b] - ref["U"]).max())
+        assert close(out["X"][b].T, ref["X"], atol=1e-4, rtol=1e-3)
+        # swing legs are exactly zero, bit for bit
+        sw = np.repeat(pb.stance[b].reshape(-1) == 0, 3)
+        assert np.all(out["U"][b].reshape(-1)[sw] == 0.0)
+    print(f"N={N} K={K} worst |dU| = {worst:.2e} N")
+
+
+def test_converged_solve_meets_reference_eps():
+    """Default settings (eps_abs = eps_rel = 1e-3 as in the reference's OSQP): every problem
+    reports solved, and the residuals recomputed independently in fp64 from the returned
+    primal/dual iterate are below the OSQP thresholds."""
+    pb = synthetic_batch(64, N=10, seed=21)
+    out = gpu_solve(pb, warm_mode=2)
+    assert np.all(out["status"] == 1)
+    assert out["iters"].max() < 1000
+    mpc = out["mpc"]
+    xw, yw = mpc.get_warm(pb.B)
+    torch.cuda.synchronize()
+    yw = yw.cpu().numpy().astype(np.float64)
+    eps = 1e-3
+    for b in range(0, 64, 4):
+        x0, r, stance, xd, mu = pb.problem(b)
+        H, g, Sc, c0, idx = srbd_qp.condensed_qp(x0, r, stance, xd, DT)
+        A = srbd_qp.constraint_rows(len(idx), mu)
+        lo, hi = ca.bounds(len(idx))
+        x = np.concatenate([out["U"][b][i, 3 * l:3 * l + 3] for (i, l) in idx])
+        y = np.concatenate([yw[b][i, l] for (i, l) in idx])
+        Ax = A @ x
+        z = np.clip(Ax, lo, hi)
+        pri = np.abs(Ax - z).max()
+        dua = np.abs(H @ x + g + A.T @ y).max()
+        eps_p = eps + eps * max(np.abs(Ax).max(), np.abs(z).max())
+        eps_d = eps + eps * max(np.abs(H @ x).max(), np.abs(A.T @ y).max(), np.abs(g).max())
+        assert pri <= 1.5 * eps_p, (b, pri, eps_p)
+        assert dua <= 1.5 * eps_d, (b, dua, eps_d)
+        # objective within 1 % of the tight optimum
+        tight = ca.solve_problem(x0, r, stance, xd, mu, DT, tight=True, rho=0.3)
+        J = srbd_qp.objective(out["X"][b].T, xd)
+        assert abs(J / tight["J"] - 1.0) < 2e-2
+
+
+def test_tight_parity_unique_quantities():
+    """Run the CUDA ADMM far past the reference's eps and compare the quantities that are
+    unique at r_weight = 0 with the tight fp64 optimum: X (1e-3 rel), objective (1e-4 rel),
+    per-stage net wrench (1e-3 rel / 1e-2 abs)."""
+    pb = synthetic_batch(24, N=10, seed=33)
+    out = gpu_solve(pb, max_iter=3000, check_every=100000, eps_abs=0.0, eps_rel=0.0, warm_mode=0)
+    ok = 0
+    for b in range(pb.B):
+        x0, r, stance, xd, mu = pb.problem(b)
+        tight = ca.solve_problem(x0, r, stance, xd, mu, DT, tight=True, rho=0.3)
+        if tight["status"] != 1 or tight["iters"] > 3000:
+            continue            # ADMM itself needs more iterations on this problem
+        ok += 1
+        J = srbd_qp.objective(out["X"][b].T, xd)
+        assert abs(J / tight["J"] - 1.0) < 1e-4, (b, J, tight["J"])
+        assert close(out["X"][b].T, tight["X"], atol=1e-5, rtol=1e-3)
+        W = srbd_qp.stage_wrench(out["U"][b], r)
+        assert close(W, tight["wrench"]), (b, np.abs(W - tight["wrench"]).max())
+    assert ok >= 12
+
+
+def test_tight_parity_forces_with_force_weight():
+    """With a force weight the optimum is unique: full forces vs tight fp64 optimum."""
+    rw = 1e-3
+    pb = synthetic_batch(16, N=10, seed=35)
+    out = gpu_solve(pb, max_iter=4000, check_every=100000, eps_abs=0.0, eps_rel=0.0, warm_mode=0,
+                    r_weight=rw)
+    ok = 0
+    for b in range(pb.B):
+        x0, r, stance, xd, mu = pb.problem(b)
+        tight = ca.solve_problem(x0, r, stance, xd, mu, DT, tight=True, rho=0.3, r_weight=rw)
+        if tight["status"] != 1 or tight["iters"] > 4000:
+            continue
+        ok += 1
+        assert close(out["U"][b], tight["U"]), (b, np.abs(out["U"][b] - tight["U"]).max())
+    assert ok >= 8
+
+
+def test_feasibility_and_masks_all_gaits():
+    """Converged forces satisfy swing / bound / friction constraints of src/mpc.py:138-173
+    (to the solver tolerance), for every gait incl. pronk flight phases and mu sweep."""
+    pb = synthetic_batch(256, N=10, gaits=GAIT_NAMES, seed=3, mu=(0.3, 1.0))
+    out = gpu_solve(pb)
+    assert np.all(out["status"] == 1)
+    F = out["U"].reshape(pb.B, 10, 4, 3)
+    st = pb.stance.astype(bool)
+    assert np.all(F[~st] == 0.0)
+    fz = F[..., 2][st]
+    mu = np.broadcast_to(pb.mu[:, None, None], st.shape)[st]
+    tol = 0.15      # eps_rel * |z| with |z| up to 100 N
+    assert fz.min() >= 3.0 - tol and fz.max() <= 100.0 + tol
+    assert np.all(np.abs(F[..., 0][st]) <= mu * fz + tol)
+    assert np.all(np.abs(F[..., 1][st]) <= mu * fz + tol)
+    # flight stages exist in the pronk problems and are all-zero
+    assert (pb.stance.sum(-1) == 0).any()
+
+
+def test_warm_start_semantics():
+    """Reference semantics (src/mpc.py:270-271): previous primal solution, unshifted; zero
+    duals.  A re-solve of the same problem from its own solution needs fewer iterations,
+    reset_warm restores the cold behaviour, set_warm/get_warm round-trip."""
+    pb = synthetic_batch(128, N=10, seed=17)
+    mpc = pkg.BatchedMPC(N=10, max_batch=128, warm_mode=1)
+    args = dev_args(pb)
+    U1, _, s1 = mpc.solve(*args)
+    it1 = s1.iters.cpu().numpy().copy()
+    U1 = U1.cpu().numpy().copy()
+    U2, _, s2 = mpc.solve(*args)
+    it2 = s2.iters.cpu().numpy().copy()
+    assert it2.mean() < it1.mean()
+    xw, yw = mpc.get_warm(128)
+    assert np.array_equal(xw.cpu().numpy(), U2.cpu().numpy())
+    mpc.reset_warm()
+    U3, _, s3 = mpc.solve(*args)
+    assert np.array_equal(s3.iters.cpu().numpy(), it1)
+    assert np.array_equal(U3.cpu().numpy(), U1)
+    # warm_mode 2 carries the duals too: immediate convergence when re-solving
+    mpc2 = pkg.BatchedMPC(N=10, max_batch=128, warm_mode=2)
+    mpc2.solve(*args)
+    _, _, s5 = mpc2.solve(*args)
+    assert s5.iters.cpu().numpy().max() <= 5
+    # set_warm on a fresh handle reproduces the warm-started solve of mpc
+    mpc3 = pkg.BatchedMPC(N=10, max_batch=128, warm_mode=1)
+    mpc3.set_warm(torch.from_numpy(U1).cuda())
+    U4, _, s4 = mpc3.solve(*args)
+    assert np.array_equal(s4.iters.cpu().numpy(), it2)
+    assert np.array_equal(U4.cpu().numpy(), U2.cpu().numpy())
+
+
+def test_host_path_matches_device_path_and_sharding():
+    """cmpc_solve_host (pinned staging, chunked streams) returns bit-identical results to
+    cmpc_solve, and solving two half batches equals solving the whole batch (problems are
+    independent - the property the multi-GPU sharding relies on)."""
+    pb = synthetic_batch(2500, N=10, gaits=GAIT_NAMES, seed=9)
+    d = gpu_solve(pb, warm_mode=0)
+    mpc = pkg.BatchedMPC(N=10, max_batch=pb.B, warm_mode=0)
+    U, X, st = mpc.solve_host(*pb.f32())
+    assert np.array_equal(U.astype(np.float64), d["U"])
+    assert np.array_equal(X.astype(np.float64), d["X"])
+    assert np.array_equal(st.iters, d["iters"]) and np.array_equal(st.status, d["status"])
+    h = pb.B // 2
+    a = gpu_solve(pb.slice(0, h), warm_mode=0)
+    b = gpu_solve(pb.slice(h, pb.B), warm_mode=0)
+    assert np.array_equal(np.concatenate([a["U"], b["U"]]), d["U"])
+    assert np.array_equal(np.concatenate([a["iters"], b["iters"]]), d["iters"])
+
+
+def test_edge_cases():
+    mpc = pkg.BatchedMPC(N=10, max_batch=8)
+    pb = synthetic_batch(8, N=10, seed=1)
+    # empty batch
+    U, X, st = mpc.solve(*[t[:0].contiguous() for t in dev_args(pb)])
+    assert U.shape == (0, 10, 12)
+    # single problem
+    U1, _, s1 = mpc.solve(*[t[:1].contiguous() for t in dev_args(pb)])
+    assert int(s1.status[0]) == 1
+    # all legs in swing for the whole horizon -> zero forces, solved in 0 iterations
+    args = dev_args(pb)
+    args[2] = torch.zeros_like(args[2])
+    mpc.reset_warm()
+    U0, X0, s0 = mpc.solve(*args)
+    assert torch.all(U0 == 0) and torch.all(s0.status == 1) and torch.all(s0.iters == 0)
+    # free fall: v_z decreases by g*dt per stage (src/mpc.py:94, A[11,12] = 1)
+    Xn = X0.cpu().numpy()
+    np.testing.assert_allclose(Xn[:, 1:, 11] - Xn[:, :-1, 11], -9.81 * 0.01, rtol=1e-4)
+    # NaN input -> status -1, other problems unaffected
+    args = dev_args(pb)
+    args[0][3, 4] = float("nan")
+    mpc.reset_warm()
+    _, _, sn = mpc.solve(*args)
+    stat = sn.status.cpu().numpy()
+    assert stat[3] == -1 and np.all(np.delete(stat, 3) == 1)
+    # batch larger than the handle
+    big = synthetic_batch(9, N=10, seed=1)
+    with pytest.raises(pkg.CmpcError):
+        mpc.solve(*dev_args(big))
+    with pytest.raises(pkg.CmpcError):
+        pkg.BatchedMPC(N=7, max_batch=4)          # no kernel for this horizon
+    with pytest.raises(pkg.CmpcError):
+        pkg.BatchedMPC(N=10, max_batch=4, w=[1, 1, 1, 1, 1, 1, 1, 2, 1, 1, 1, 1, 0])
+
+
+def test_full_size_properties_batch_4096():
+    """BASELINE.json config 2 at full size (4096 trot problems, N=10): size-independent
+    properties - all solved, dynamics consistency of the returned X with the returned U
+    (forward-Euler recursion of src/mpc.py:113-117 in fp64), permutation invariance."""
+    pb = synthetic_batch(4096, N=10, seed=0)
+    out = gpu_solve(pb, warm_mode=0)
+    assert np.all(out["status"] == 1)
+    rng = np.random.default_rng(0)
+    for b in rng.integers(0, 4096, 12):
+        x0, r, stance, xd, mu = pb.problem(b)
+        x0, r = np.float32(x0).astype(np.float64), np.float32(r).astype(np.float64)
+        X = np.zeros((13, 11))
+        X[:, 0] = x0
+        Ad = np.eye(13) + DT * srbd_qp.continuous_A(x0[2])
+        for i in range(10):
+            X[:, i + 1] = Ad @ X[:, i] + DT * srbd_qp.continuous_B(x0[2], r[i]) @ out["U"][b][i]
+        assert close(out["X"][b].T, X, atol=2e-5, rtol=1e-4)
+    perm = rng.permutation(4096)
+    pb2 = pkg.problems.ProblemBatch(pb.x0[perm], pb.r[perm], pb.stance[perm], pb.x_des[perm],
+                                    pb.mu[perm], pb.gait_id[perm], pb.tick[perm])
+    out2 = gpu_solve(pb2, warm_mode=0)
+    assert np.array_equal(out2["U"], out["U"][perm])

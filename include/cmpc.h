@@ -77,6 +77,11 @@ typedef struct cmpc_config {
   int32_t check_every;  /* termination test period                                   */
   int32_t refresh_every;/* exact recomputation period of the wrench-space gradient   */
   int32_t warm_mode;    /* CMPC_WARM_*                                               */
+  int32_t adaptive_rho_interval; /* OSQP-style rho adaptation every k iterations, 0 = off */
+  float adaptive_rho_tolerance;  /* refactor when rho changes by more than this factor (5) */
+  float rho_min, rho_max;        /* clamp of the adapted rho                                 */
+  int32_t kernel_variant; /* 0 = default thread layout; >0 selects an alternative (more threads
+                             per problem) where one is compiled, see DESIGN.md            */
   int32_t device;       /* CUDA device ordinal                                       */
 } cmpc_config;
 

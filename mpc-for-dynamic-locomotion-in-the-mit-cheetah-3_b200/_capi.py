@@ -39,7 +39,10 @@ class Config(C.Structure):
                 ("f_min", C.c_float), ("f_max", C.c_float), ("rho", C.c_float),
                 ("sigma", C.c_float), ("alpha", C.c_float), ("eps_abs", C.c_float),
                 ("eps_rel", C.c_float), ("max_iter", C.c_int32), ("check_every", C.c_int32),
-                ("refresh_every", C.c_int32), ("warm_mode", C.c_int32), ("device", C.c_int32)]
+                ("refresh_every", C.c_int32), ("warm_mode", C.c_int32),
+                ("adaptive_rho_interval", C.c_int32), ("adaptive_rho_tolerance", C.c_float),
+                ("rho_min", C.c_float), ("rho_max", C.c_float),
+                ("kernel_variant", C.c_int32), ("device", C.c_int32)]
 
 
 def needs_build() -> bool:

@@ -93,27 +93,33 @@ cudaError_t launch_condense(const cmpc::CondenseParams& p, cudaStream_t s) {
 
 struct HorizonEntry {
   int N;
-  SolveLaunch solve;
+  SolveLaunch solve[3];      // thread-layout variants (nullptr = not compiled)
   CondenseLaunch condense;
 };
 
 // Horizons with compiled kernels.  <N, SPLIT, MINB>: SPLIT threads share one row of the
 // 6N x 6N wrench matrix so that the register-resident row slice stays <= 60 floats.
 const HorizonEntry kHorizons[] = {
-    {4, launch_solve<4, 1, 8>, launch_condense<4>},
-    {5, launch_solve<5, 1, 8>, launch_condense<5>},
-    {8, launch_solve<8, 1, 8>, launch_condense<8>},
-    {10, launch_solve<10, 1, 8>, launch_condense<10>},
-    {12, launch_solve<12, 2, 4>, launch_condense<12>},
-    {16, launch_solve<16, 2, 3>, launch_condense<16>},
-    {20, launch_solve<20, 2, 2>, launch_condense<20>},
-    {30, launch_solve<30, 4, 1>, launch_condense<30>},
+    {4, {launch_solve<4, 1, 8>, nullptr, nullptr}, launch_condense<4>},
+    {5, {launch_solve<5, 1, 8>, nullptr, nullptr}, launch_condense<5>},
+    {8, {launch_solve<8, 1, 8>, nullptr, nullptr}, launch_condense<8>},
+    {10, {launch_solve<10, 1, 8>, launch_solve<10, 2, 4>, launch_solve<10, 4, 2>}, launch_condense<10>},
+    {12, {launch_solve<12, 2, 4>, nullptr, nullptr}, launch_condense<12>},
+    {16, {launch_solve<16, 2, 3>, nullptr, nullptr}, launch_condense<16>},
+    {20, {launch_solve<20, 2, 2>, nullptr, nullptr}, launch_condense<20>},
+    {30, {launch_solve<30, 4, 1>, nullptr, nullptr}, launch_condense<30>},
 };
 
 const HorizonEntry* find_horizon(int N) {
   for (const auto& e : kHorizons)
     if (e.N == N) return &e;
   return nullptr;
+}
+
+SolveLaunch pick_solve(const cmpc_config& c) {
+  const HorizonEntry* e = find_horizon(c.N);
+  const int v = (c.kernel_variant >= 0 && c.kernel_variant < 3) ? c.kernel_variant : 0;
+  return e->solve[v] ? e->solve[v] : e->solve[0];
 }
 
 void fill_solve_params(const cmpc_handle* h, cmpc::SolveParams& p) {
@@ -139,6 +145,10 @@ void fill_solve_params(const cmpc_handle* h, cmpc::SolveParams& p) {
   p.check_every = c.check_every;
   p.refresh_every = c.refresh_every;
   p.warm_mode = c.warm_mode;
+  p.adaptive_rho_interval = c.adaptive_rho_interval;
+  p.adaptive_rho_tolerance = c.adaptive_rho_tolerance;
+  p.rho_min = c.rho_min;
+  p.rho_max = c.rho_max;
 }
 
 int check_batch(const cmpc_handle* h, int B, int slot0) {
@@ -189,8 +199,12 @@ int cmpc_default_config(cmpc_config* cfg, int32_t N, int32_t max_batch) {
   cfg->eps_rel = 1e-3f;
   cfg->max_iter = 1000;                 // src/mpc.py:51
   cfg->check_every = 5;
-  cfg->refresh_every = 25;
+  cfg->refresh_every = 5;
   cfg->warm_mode = CMPC_WARM_PRIMAL;
+  cfg->adaptive_rho_interval = 25;      // OSQP adapts rho too (adaptive_rho = 1 by default)
+  cfg->adaptive_rho_tolerance = 3.0f;
+  cfg->rho_min = 0.03f;                 // fp32 Woodbury form loses accuracy for rho << |H|
+  cfg->rho_max = 30.0f;
   cfg->device = 0;
   return CMPC_OK;
 }
@@ -208,6 +222,9 @@ int cmpc_create(const cmpc_config* cfg, cmpc_handle** out) {
   if (c.max_iter < 0 || c.check_every <= 0 || c.refresh_every < 0)
     return fail(CMPC_ERR_INVALID, "max_iter >= 0, check_every > 0, refresh_every >= 0 required");
   if (c.warm_mode < 0 || c.warm_mode > 2) return fail(CMPC_ERR_INVALID, "bad warm_mode");
+  if (c.adaptive_rho_interval < 0 || (c.adaptive_rho_interval > 0 && !(c.adaptive_rho_tolerance > 1.f)))
+    return fail(CMPC_ERR_INVALID, "adaptive_rho_interval >= 0 and adaptive_rho_tolerance > 1 required");
+  if (!(c.rho_min > 0.f) || !(c.rho_min <= c.rho_max)) return fail(CMPC_ERR_INVALID, "0 < rho_min <= rho_max required");
   for (int i = 0; i < 12; ++i)
     if (!(c.w[i] >= 0)) return fail(CMPC_ERR_INVALID, "state weights must be >= 0");
   if (c.w[6] != c.w[7])
@@ -311,7 +328,7 @@ int cmpc_solve(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, const 
   p.U = U; p.X = X; p.iters = iters; p.pri_res = pri_res; p.dua_res = dua_res; p.status = status;
   p.B = B;
   p.slot0 = slot0;
-  CUDA_TRY(find_horizon(h->cfg.N)->solve(p, (cudaStream_t)stream));
+  CUDA_TRY(pick_solve(h->cfg)(p, (cudaStream_t)stream));
   h->launches.fetch_add(1);
   return CMPC_OK;
 }
@@ -400,7 +417,7 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, c
   const Layout La = make_layout(N, st.cap, true);   // arena strides use the allocated capacity
   cmpc::SolveParams base{};
   fill_solve_params(h, base);
-  const HorizonEntry* he = find_horizon(N);
+  const SolveLaunch solve_fn = pick_solve(h->cfg);
   for (int ci = 0; ci < nchunk; ++ci) {
     const int lo = ci * C, n = (lo + C <= B ? C : B - lo);
     if (n <= 0) break;
@@ -429,7 +446,7 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, c
     p.status = (int32_t*)(dout + La.status);
     p.B = n;
     p.slot0 = slot0 + lo;
-    CUDA_TRY(he->solve(p, s));
+    CUDA_TRY(solve_fn(p, s));
     h->launches.fetch_add(1);
     const size_t out_n = X ? La.out_total : La.X;
     CUDA_TRY(cudaMemcpyAsync(hout, dout, out_n, cudaMemcpyDeviceToHost, s));

@@ -49,6 +49,9 @@ struct SolveParams {
   float w[13];
   float r_weight, f_min, f_max, rho, sigma, alpha, eps_abs, eps_rel;
   int32_t max_iter, check_every, refresh_every, warm_mode;
+  int32_t adaptive_rho_interval;      // 0 = fixed rho
+  float adaptive_rho_tolerance;
+  float rho_min, rho_max;             // clamp of the adapted rho (fp32 stability of the Woodbury form)
 };
 
 template <int N, int SPLIT>
@@ -61,6 +64,7 @@ struct Geo {
   static constexpr int TMAX = ROWT > NLEG ? ROWT : NLEG;
   static constexpr int THREADS = ((TMAX + 31) / 32) * 32;
   static constexpr int WARPS = THREADS / 32;
+  static constexpr int LWARPS = (NLEG + 31) / 32;                   // warps that own leg threads
   static constexpr int NX = 13 * (N + 1);
 };
 
@@ -121,20 +125,20 @@ __device__ __forceinline__ float wrench_linear_term(int j, int a, const float* s
     if (a < 3) {
       const float rw0 = a == 0 ? rw0x : (a == 1 ? rw0y : rw0z);
       const float rwd = a == 0 ? (c * xd[6] - s * xd[7]) : (a == 1 ? (s * xd[6] + c * xd[7]) : xd[8]);
-      e_pos = sx0[a] + kf * dt * rw0 - xd[a];
+      e_pos = (sx0[a] - xd[a]) + kf * dt * rw0;      // exact difference first
       e_vel = rw0 - rwd;
       wp = w[a];
       wv = w[6 + a];
     } else {
       const int aa = a - 3;
-      float pf = sx0[3 + aa] + kf * dt * sx0[9 + aa];
-      float vf = sx0[9 + aa];
+      float pf = (sx0[3 + aa] - xd[3 + aa]) + kf * dt * sx0[9 + aa];
+      float vf = sx0[9 + aa] - xd[9 + aa];
       if (aa == 2) {
         pf += 0.5f * kf * (kf - 1.f) * dt * dt * g;
         vf += kf * dt * g;
       }
-      e_pos = pf - xd[3 + aa];
-      e_vel = vf - xd[9 + aa];
+      e_pos = pf;
+      e_vel = vf;
       wp = w[3 + aa];
       wv = w[9 + aa];
     }
@@ -151,7 +155,7 @@ __global__ void __launch_bounds__(Geo<N, SPLIT>::THREADS, MINB)
 solve_kernel(const SolveParams p) {
   using G_ = Geo<N, SPLIT>;
   constexpr int NW = G_::NW, NWP = G_::NWP, COLS = G_::COLS, NLEG = G_::NLEG;
-  constexpr int THREADS = G_::THREADS, WARPS = G_::WARPS, NX = G_::NX;
+  constexpr int THREADS = G_::THREADS, LWARPS = G_::LWARPS, NX = G_::NX;
 
   __shared__ __align__(16) float s_x0[16];
   __shared__ __align__(16) float s_xd[NX + 3];
@@ -160,13 +164,14 @@ solve_kernel(const SolveParams p) {
   __shared__ __align__(16) float s_s[NWP];             // wrench-space rhs  s = G D^-1 b
   __shared__ __align__(16) float s_q[NWP];             // q = P^-1 s   (also: w, v scratch)
   __shared__ __align__(16) float s_h[NWP];             // linear term h
-  __shared__ float s_red[2][WARPS][8];
+  __shared__ float s_red[2][LWARPS][8];
   __shared__ int s_mask[N];
 
   const int b = blockIdx.x;
   if (b >= p.B) return;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
+  const bool leg_warp = warp < LWARPS;   // warp-uniform: warps without leg threads skip leg phases
   const int slot = p.slot0 + b;
 
   // ---- phase 0: stage the per-problem record (coalesced 4-byte loads) -------------------
@@ -175,16 +180,35 @@ solve_kernel(const SolveParams p) {
   for (int i = tid; i < N; i += THREADS) s_mask[i] = (int)__ldg(p.mask + (size_t)b * N + i);
   for (int i = tid; i < NWP; i += THREADS) { s_s[i] = 0.f; s_q[i] = 0.f; s_h[i] = 0.f; }
   const float mu = __ldg(p.mu + b);
+  // issue every other global load of this problem now so that their DRAM latencies overlap
+  const bool is_leg = tid < NLEG;
+  float r_in[3] = {0.f, 0.f, 0.f};
+  float wx_in[3] = {0.f, 0.f, 0.f};
+  float wy_in[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  const bool warm = p.warm_mode != 0 && p.warm_valid[slot] != 0;
+  if (is_leg) {
+    const float* rp = p.r + ((size_t)b * NLEG + tid) * 3;
+    r_in[0] = __ldg(rp); r_in[1] = __ldg(rp + 1); r_in[2] = __ldg(rp + 2);
+    if (warm) {
+      const float* wx = p.warm_x + ((size_t)slot * NLEG + tid) * 3;
+      wx_in[0] = wx[0]; wx_in[1] = wx[1]; wx_in[2] = wx[2];
+      if (p.warm_mode == 2) {
+        const float* wy = p.warm_y + ((size_t)slot * NLEG + tid) * 5;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) wy_in[k] = wy[k];
+      }
+    }
+  }
   __syncthreads();
 
   float sn, cs;
   sincosf(s_x0[2], &sn, &cs);
   const float im = p.inv_mass;
-  const float rho = p.rho, alpha = p.alpha;
-  const float rho_inv = 1.f / rho;
+  const float alpha = p.alpha;
+  float rho = p.rho;
+  float rho_inv = 1.f / rho;
 
   // ---- phase 1: leg geometry, linear term -----------------------------------------------
-  const bool is_leg = tid < NLEG;
   const int lj = tid >> 2, ll = tid & 3;            // stage, leg of a leg thread
   bool stance = false;
   float Gh[3][3];
@@ -195,13 +219,8 @@ solve_kernel(const SolveParams p) {
     for (int k = 0; k < 3; ++k) Gh[a][k] = 0.f;
   if (is_leg) {
     stance = (s_mask[lj] >> ll) & 1;
-    const float* rp = p.r + ((size_t)b * NLEG + tid) * 3;
-    const float rx = __ldg(rp), ry = __ldg(rp + 1), rz = __ldg(rp + 2);
-    leg_map(cs, sn, p.ib, rx, ry, rz, Gh);
-    if (stance) {
-      dxy = 1.f / (p.sigma + 2.f * p.r_weight + 2.f * rho);
-      dz = 1.f / (p.sigma + 2.f * p.r_weight + rho * (1.f + 4.f * mu * mu));
-    } else {
+    leg_map(cs, sn, p.ib, r_in[0], r_in[1], r_in[2], Gh);
+    if (!stance) {
 #pragma unroll
       for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -211,8 +230,6 @@ solve_kernel(const SolveParams p) {
     for (int a = 0; a < 3; ++a)
 #pragma unroll
       for (int k = 0; k < 3; ++k) s_G[tid][3 * a + k] = Gh[a][k];
-    s_G[tid][9] = dxy;
-    s_G[tid][10] = dz;
     s_G[tid][11] = stance ? 1.f : 0.f;
   }
   const bool is_row = tid < G_::ROWT;
@@ -221,8 +238,18 @@ solve_kernel(const SolveParams p) {
   if (is_row && rs == 0) s_h[ri] = wrench_linear_term<N>(rj, ra, s_x0, s_xd, cs, sn, p.w, p.dt);
   __syncthreads();
 
-  // ---- phase 2: P = M^-1 + E (row slices in registers) ------------------------------------
+  // ---- phases 2+3 as a re-runnable step (adaptive rho refactorises) ------------------------
   float row[COLS];
+  auto factorize = [&]() {
+  // D^-1 of this leg for the current rho (A'A = diag(2, 2, 1 + 4 mu^2) per stance leg)
+  dxy = stance ? 1.f / (p.sigma + 2.f * p.r_weight + 2.f * rho) : 0.f;
+  dz = stance ? 1.f / (p.sigma + 2.f * p.r_weight + rho * (1.f + 4.f * mu * mu)) : 0.f;
+  if (is_leg) {
+    s_G[tid][9] = dxy;
+    s_G[tid][10] = dz;
+  }
+  __syncthreads();
+  // ---- phase 2: P = M^-1 + E (row slices in registers) ------------------------------------
 #pragma unroll
   for (int c = 0; c < COLS; ++c) row[c] = 0.f;
   if (is_row) {
@@ -298,6 +325,8 @@ solve_kernel(const SolveParams p) {
     }
   }
   __syncthreads();
+  };
+  factorize();
 
   // ---- phase 4: initial iterate -----------------------------------------------------------
   float x[3] = {0.f, 0.f, 0.f};
@@ -305,20 +334,15 @@ solve_kernel(const SolveParams p) {
   float z[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   float gl[3] = {0.f, 0.f, 0.f};          // linear term of this leg:  G' h
   float vj[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // wrench-space gradient v = M G x of this stage
-  const bool warm = p.warm_mode != 0 && p.warm_valid[slot] != 0;
   if (is_leg && stance) {
     const float* hj = s_h + 6 * lj;
 #pragma unroll
     for (int k = 0; k < 3; ++k)
       gl[k] = Gh[0][k] * hj[0] + Gh[1][k] * hj[1] + Gh[2][k] * hj[2] + im * hj[3 + k];
     if (warm) {
-      const float* wx = p.warm_x + ((size_t)slot * NLEG + tid) * 3;
-      x[0] = wx[0]; x[1] = wx[1]; x[2] = wx[2];
-      if (p.warm_mode == 2) {
-        const float* wy = p.warm_y + ((size_t)slot * NLEG + tid) * 5;
+      x[0] = wx_in[0]; x[1] = wx_in[1]; x[2] = wx_in[2];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) y[k] = wy[k];
-      }
+      for (int k = 0; k < 5; ++k) y[k] = wy_in[k];
     }
     z[0] = fminf(fmaxf(x[2], p.f_min), p.f_max);
     z[1] = fminf(x[0] - mu * x[2], 0.f);
@@ -329,14 +353,15 @@ solve_kernel(const SolveParams p) {
 
   // exact wrench-space gradient  v = M (G x)  (uniform: every thread takes part)
   auto refresh_gradient = [&]() {
-    if (is_leg) {
+    if (leg_warp) {   // whole warps: every lane executes the shuffles (Gh = x = 0 on non-leg lanes)
       float wv[6];
 #pragma unroll
       for (int a = 0; a < 3; ++a)
         wv[a] = quad_sum(Gh[a][0] * x[0] + Gh[a][1] * x[1] + Gh[a][2] * x[2]);
 #pragma unroll
       for (int k = 0; k < 3; ++k) wv[3 + k] = quad_sum(x[k] * im);
-      if (ll < 3) *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = make_float2(wv[2 * ll], wv[2 * ll + 1]);
+      if (is_leg && ll < 3)
+        *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = make_float2(wv[2 * ll], wv[2 * ll + 1]);
     }
     __syncthreads();
     if (is_row && rs == 0) {
@@ -359,26 +384,38 @@ solve_kernel(const SolveParams p) {
   float ng = 0.f;
   {
     float m = fmaxf(fabsf(gl[0]), fmaxf(fabsf(gl[1]), fabsf(gl[2])));
-    m = warp_max_nonneg(m);
-    if (lane == 0) s_red[1][warp][0] = m;
+    if (leg_warp) {
+      m = warp_max_nonneg(m);
+      if (lane == 0) s_red[1][warp][0] = m;
+    }
     __syncthreads();
 #pragma unroll
-    for (int wv = 0; wv < WARPS; ++wv) ng = fmaxf(ng, s_red[1][wv][0]);
+    for (int wv = 0; wv < LWARPS; ++wv) ng = fmaxf(ng, s_red[1][wv][0]);
     __syncthreads();
   }
 
   // ---- phase 5: ADMM ------------------------------------------------------------------------
   int it = 0;
   int status = 0;
+  int rho_updates = 0;
+  int next_chk = 0;
+  int next_ref = p.refresh_every > 0 ? p.refresh_every : -1;
+  int next_adp = p.adaptive_rho_interval > 0 ? p.adaptive_rho_interval : -1;
   float pri = 0.f, dua = 0.f;
   const float two_rw = 2.f * p.r_weight;
   for (;;) {
-    if (p.refresh_every > 0 && it > 0 && (it % p.refresh_every) == 0) refresh_gradient();
+    if (it == next_ref) {
+      next_ref += p.refresh_every;
+      refresh_gradient();
+    }
     // leg phase A: residuals of the current iterate, rhs of the correction equation
     float t[3] = {0.f, 0.f, 0.f};
-    const bool chk = (it % p.check_every) == 0 || it >= p.max_iter;
+    const bool adapt_now = it == next_adp;
+    if (adapt_now) next_adp += p.adaptive_rho_interval;
+    const bool chk = it == next_chk || it >= p.max_iter || adapt_now;
+    if (it == next_chk) next_chk += p.check_every;
     float st_[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (is_leg) {
+    if (leg_warp) {   // whole warps (all-zero state on non-leg lanes) so the shuffles are convergent
       float Ax[5], Aty[3], Hx[3], rd[3], rp[5];
       Ax[0] = x[2];
       Ax[1] = x[0] - mu * x[2];
@@ -412,7 +449,8 @@ solve_kernel(const SolveParams p) {
         sv[a] = quad_sum(Gh[a][0] * t[0] + Gh[a][1] * t[1] + Gh[a][2] * t[2]);
 #pragma unroll
       for (int k = 0; k < 3; ++k) sv[3 + k] = quad_sum(t[k] * im);
-      if (ll < 3) *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = make_float2(sv[2 * ll], sv[2 * ll + 1]);
+      if (is_leg && ll < 3)
+        *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = make_float2(sv[2 * ll], sv[2 * ll + 1]);
       if (chk) {
         float m;
         m = 0.f;
@@ -428,12 +466,12 @@ solve_kernel(const SolveParams p) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) m = fmaxf(m, fmaxf(fabsf(Hx[k]), fabsf(Aty[k])));
         st_[3] = m;                                            // max(|Hx|,|A'y|)
-        // NaN guard: a NaN anywhere makes the sum NaN
-        st_[4] = fabsf((x[0] + x[1] + x[2]) * 0.f);
+        // NaN / Inf guard: any non-finite value makes the product NaN
+        st_[4] = fabsf((x[0] + x[1] + x[2] + rd[0] + rd[1] + rd[2]) * 0.f);
       }
     }
-    if (chk) {
-      const int pb = (it / p.check_every) & 1;
+    if (chk && leg_warp) {
+      const int pb = 0;
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
         const float m = warp_max_nonneg(st_[k]);
@@ -442,10 +480,10 @@ solve_kernel(const SolveParams p) {
     }
     __syncthreads();
     if (chk) {
-      const int pb = (it / p.check_every) & 1;
+      const int pb = 0;
       float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, m4 = 0.f;
 #pragma unroll
-      for (int wv = 0; wv < WARPS; ++wv) {
+      for (int wv = 0; wv < LWARPS; ++wv) {
         m0 = fmaxf(m0, s_red[pb][wv][0]);
         m1 = fmaxf(m1, s_red[pb][wv][1]);
         m2 = fmaxf(m2, s_red[pb][wv][2]);
@@ -459,28 +497,40 @@ solve_kernel(const SolveParams p) {
       if (!(m4 == 0.f) || !(m0 == m0) || !(m1 == m1)) { status = -1; break; }
       if (pri <= eps_p && dua <= eps_d) { status = 1; break; }
       if (it >= p.max_iter) { status = 0; break; }
+      if (adapt_now) {
+        // OSQP's rho adaptation: balance the normalised primal and dual residuals
+        const float pr_n = m0 / (m2 + 1e-10f);
+        const float du_n = m1 / (fmaxf(m3, ng) + 1e-10f);
+        float rn = rho * sqrtf(pr_n / (du_n + 1e-10f));
+        rn = fminf(fmaxf(rn, p.rho_min), p.rho_max);
+        if (rn > rho * p.adaptive_rho_tolerance || rn * p.adaptive_rho_tolerance < rho) {
+          rho = rn;
+          rho_inv = 1.f / rho;
+          ++rho_updates;
+          factorize();     // uniform: every thread of the CTA sees the same statistics
+          continue;        // redo phase A of this iterate with the new rho
+        }
+      }
     }
     // wrench phase: q = P^-1 s   (row holds -P^-1)
-    if (is_row) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      const float* sp = s_s + rs * COLS;
+    {
+      float acc = 0.f;
+      if (is_row) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float* sp = s_s + rs * COLS;
 #pragma unroll
-      for (int c = 0; c < COLS; c += 4) {
-        const float4 sv4 = *reinterpret_cast<const float4*>(sp + c);
-        a0 = fmaf(row[c], sv4.x, a0);
-        a1 = fmaf(row[c + 1], sv4.y, a1);
-        a2 = fmaf(row[c + 2], sv4.z, a2);
-        a3 = fmaf(row[c + 3], sv4.w, a3);
+        for (int c = 0; c < COLS; c += 4) {
+          const float4 sv4 = *reinterpret_cast<const float4*>(sp + c);
+          a0 = fmaf(row[c], sv4.x, a0);
+          a1 = fmaf(row[c + 1], sv4.y, a1);
+          a2 = fmaf(row[c + 2], sv4.z, a2);
+          a3 = fmaf(row[c + 3], sv4.w, a3);
+        }
+        acc = (a0 + a1) + (a2 + a3);
       }
-      float acc = (a0 + a1) + (a2 + a3);
       if (SPLIT >= 2) acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       if (SPLIT >= 4) acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      if (rs == 0) s_q[ri] = -acc;
-    } else if (SPLIT >= 2) {
-      // keep whole warps converged for the shuffles above
-      float acc = 0.f;
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      if (SPLIT >= 4) acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (is_row && rs == 0) s_q[ri] = -acc;
     }
     __syncthreads();
     // leg phase B: x += alpha d, relaxed projection, dual update
@@ -536,14 +586,15 @@ solve_kernel(const SolveParams p) {
   if (p.X) {
     // predicted states X = free response + forced response of the wrench sequence w = G x
     __syncthreads();
-    if (is_leg) {
+    if (leg_warp) {
       float wv[6];
 #pragma unroll
       for (int a = 0; a < 3; ++a)
         wv[a] = quad_sum(Gh[a][0] * x[0] + Gh[a][1] * x[1] + Gh[a][2] * x[2]);
 #pragma unroll
       for (int k = 0; k < 3; ++k) wv[3 + k] = quad_sum(x[k] * im);
-      if (ll < 3) *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = make_float2(wv[2 * ll], wv[2 * ll + 1]);
+      if (is_leg && ll < 3)
+        *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = make_float2(wv[2 * ll], wv[2 * ll + 1]);
     }
     __syncthreads();
     const float dt = p.dt, g = s_x0[12];

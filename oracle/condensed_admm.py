@@ -25,12 +25,14 @@ def bounds(n_legs, f_min=srbd_qp.F_MIN, f_max=srbd_qp.F_MAX):
     return lo, hi
 
 
-def admm(H, g, mu, rho=0.1, sigma=1e-6, alpha=1.6, eps_abs=1e-3, eps_rel=1e-3,
+def admm(H, g, mu, rho=0.3, sigma=1e-6, alpha=1.6, eps_abs=1e-3, eps_rel=1e-3,
          max_iter=1000, check_every=5, x=None, y=None, f_min=srbd_qp.F_MIN,
-         f_max=srbd_qp.F_MAX, dtype=np.float64, fixed_iters=None):
+         f_max=srbd_qp.F_MAX, dtype=np.float64, fixed_iters=None, adaptive_interval=0,
+         adaptive_tolerance=5.0):
     """OSQP-style ADMM with a single rho, no scaling.  Returns dict(x, y, z, iters,
     pri_res, dua_res, status).  ``fixed_iters`` runs exactly that many iterations (for
-    iterate-level parity with the CUDA kernel)."""
+    iterate-level parity with the CUDA kernel).  ``adaptive_interval`` > 0 applies OSQP's rho
+    adaptation rule every that many iterations (refactorising K), as the CUDA kernel does."""
     n = H.shape[0]
     S = n // 3
     dt = dtype
@@ -43,10 +45,15 @@ def admm(H, g, mu, rho=0.1, sigma=1e-6, alpha=1.6, eps_abs=1e-3, eps_rel=1e-3,
     y = np.zeros(5 * S, dt) if y is None else y.astype(dt)
     z = np.clip(A @ x, lo, hi)
     rho, sigma, alpha = dt(rho), dt(sigma), dt(alpha)
-    K = H + sigma * np.eye(n, dtype=dt) + rho * (A.T @ A)
-    if n:
-        L = np.linalg.cholesky(K.astype(np.float64)).astype(dt) if dt == np.float64 \
+    AtA = A.T @ A
+
+    def factor(rho_):
+        K = H + sigma * np.eye(n, dtype=dt) + rho_ * AtA
+        return np.linalg.cholesky(K.astype(np.float64)).astype(dt) if dt == np.float64 \
             else _chol32(K)
+    if n:
+        L = factor(rho)
+    rho_updates = 0
     status, it = 0, 0
     pri = dua = dt(0)
     total = fixed_iters if fixed_iters is not None else max_iter
@@ -59,7 +66,8 @@ def admm(H, g, mu, rho=0.1, sigma=1e-6, alpha=1.6, eps_abs=1e-3, eps_rel=1e-3,
         zn = np.clip(zh + y / rho, lo, hi)
         y = y + rho * (zh - zn)
         z = zn
-        if fixed_iters is None and it % check_every == 0:
+        adapt = adaptive_interval > 0 and it % adaptive_interval == 0
+        if (fixed_iters is None and it % check_every == 0) or adapt:
             Ax = A @ x
             Hx = H @ x
             Aty = A.T @ y
@@ -67,14 +75,23 @@ def admm(H, g, mu, rho=0.1, sigma=1e-6, alpha=1.6, eps_abs=1e-3, eps_rel=1e-3,
             dua = np.max(np.abs(Hx + g + Aty)) if n else dt(0)
             eps_p = eps_abs + eps_rel * max(_inf(Ax), _inf(z))
             eps_d = eps_abs + eps_rel * max(_inf(Hx), _inf(Aty), _inf(g))
-            if pri <= eps_p and dua <= eps_d:
+            if fixed_iters is None and pri <= eps_p and dua <= eps_d:
                 status = 1
                 break
+            if adapt and n:
+                pr_n = pri / (max(_inf(Ax), _inf(z)) + 1e-10)
+                du_n = dua / (max(_inf(Hx), _inf(Aty), _inf(g)) + 1e-10)
+                rn = min(max(float(rho) * np.sqrt(pr_n / (du_n + 1e-10)), 1e-6), 1e6)
+                if rn > float(rho) * adaptive_tolerance or rn * adaptive_tolerance < float(rho):
+                    rho = dt(rn)
+                    L = factor(rho)
+                    rho_updates += 1
     if fixed_iters is not None or status == 0:
         Ax, Hx, Aty = A @ x, H @ x, A.T @ y
         pri = np.max(np.abs(Ax - z)) if n else dt(0)
         dua = np.max(np.abs(Hx + g + Aty)) if n else dt(0)
-    return dict(x=x, y=y, z=z, iters=it, pri_res=float(pri), dua_res=float(dua), status=status)
+    return dict(x=x, y=y, z=z, iters=it, pri_res=float(pri), dua_res=float(dua), status=status,
+                rho=float(rho), rho_updates=rho_updates)
 
 
 def _inf(v):
@@ -106,7 +123,8 @@ def solve_problem(x0, r, stance, x_des, mu, delta, tight=False, r_weight=0.0, **
     N = r.shape[0]
     H, gvec, Sc, c0, idx = srbd_qp.condensed_qp(x0, r, stance, x_des, delta, r_weight=r_weight)
     if tight:
-        kw = dict(dict(eps_abs=1e-9, eps_rel=1e-9, max_iter=200000, check_every=25), **kw)
+        kw = dict(dict(eps_abs=1e-9, eps_rel=1e-9, max_iter=200000, check_every=25,
+                       adaptive_interval=100), **kw)
     info = admm(H, gvec, mu, **kw)
     U = np.zeros((N, 12))
     for s, (i, l) in enumerate(idx):

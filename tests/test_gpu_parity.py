@@ -84,7 +84,8 @@ def test_condense_matches_oracle(N, gaits):
 def test_iterate_parity_fixed_iterations(N, gaits, B, K):
     """Same ADMM, same iteration count: fp32 CUDA vs fp64 oracle, full force vector."""
     pb = synthetic_batch(B, N=N, gaits=gaits, seed=5)
-    out = gpu_solve(pb, max_iter=K, check_every=100000, eps_abs=0.0, eps_rel=0.0, warm_mode=0)
+    out = gpu_solve(pb, max_iter=K, check_every=100000, eps_abs=0.0, eps_rel=0.0, warm_mode=0,
+                    adaptive_rho_interval=0)
     assert np.all(out["iters"] == K) and np.all(out["status"] == 0)
     worst = 0.0
     for b in range(B):
@@ -133,37 +134,41 @@ def test_converged_solve_meets_reference_eps():
 
 
 def test_tight_parity_unique_quantities():
-    """Run the CUDA ADMM far past the reference's eps and compare the quantities that are
-    unique at r_weight = 0 with the tight fp64 optimum: X (1e-3 rel), objective (1e-4 rel),
-    per-stage net wrench (1e-3 rel / 1e-2 abs)."""
+    """Run the CUDA ADMM far past the reference's eps (3000 iterations, no early exit) and
+    compare the quantities that are unique at r_weight = 0 with the tight fp64 optimum:
+    X (1e-3 rel / 5e-5 abs), objective (1e-4 rel), per-stage net wrench (1e-3 rel / 1e-2 N)."""
     pb = synthetic_batch(24, N=10, seed=33)
-    out = gpu_solve(pb, max_iter=3000, check_every=100000, eps_abs=0.0, eps_rel=0.0, warm_mode=0)
+    out = gpu_solve(pb, max_iter=3000, check_every=25, eps_abs=0.0, eps_rel=0.0, warm_mode=0)
     ok = 0
     for b in range(pb.B):
         x0, r, stance, xd, mu = pb.problem(b)
-        tight = ca.solve_problem(x0, r, stance, xd, mu, DT, tight=True, rho=0.3)
-        if tight["status"] != 1 or tight["iters"] > 3000:
+        tight = ca.solve_problem(x0, r, stance, xd, mu, DT, tight=True, rho=0.3,
+                                 adaptive_interval=25, adaptive_tolerance=3.0)
+        if tight["status"] != 1 or tight["iters"] > 1500:
             continue            # ADMM itself needs more iterations on this problem
         ok += 1
         J = srbd_qp.objective(out["X"][b].T, xd)
         assert abs(J / tight["J"] - 1.0) < 1e-4, (b, J, tight["J"])
-        assert close(out["X"][b].T, tight["X"], atol=1e-5, rtol=1e-3)
+        assert close(out["X"][b].T, tight["X"], atol=5e-5, rtol=1e-3), \
+            (b, np.abs(out["X"][b].T - tight["X"]).max())
         W = srbd_qp.stage_wrench(out["U"][b], r)
         assert close(W, tight["wrench"]), (b, np.abs(W - tight["wrench"]).max())
     assert ok >= 12
 
 
 def test_tight_parity_forces_with_force_weight():
-    """With a force weight the optimum is unique: full forces vs tight fp64 optimum."""
-    rw = 1e-3
+    """With a force weight the optimum is unique: full forces vs the tight fp64 optimum,
+    |dU| <= 1e-2 N + 1e-3 |U|  (the north-star tolerance)."""
+    rw = 1e-2
     pb = synthetic_batch(16, N=10, seed=35)
-    out = gpu_solve(pb, max_iter=4000, check_every=100000, eps_abs=0.0, eps_rel=0.0, warm_mode=0,
+    out = gpu_solve(pb, max_iter=4000, check_every=25, eps_abs=0.0, eps_rel=0.0, warm_mode=0,
                     r_weight=rw)
     ok = 0
     for b in range(pb.B):
         x0, r, stance, xd, mu = pb.problem(b)
-        tight = ca.solve_problem(x0, r, stance, xd, mu, DT, tight=True, rho=0.3, r_weight=rw)
-        if tight["status"] != 1 or tight["iters"] > 4000:
+        tight = ca.solve_problem(x0, r, stance, xd, mu, DT, tight=True, rho=0.3, r_weight=rw,
+                                 adaptive_interval=25, adaptive_tolerance=3.0)
+        if tight["status"] != 1 or tight["iters"] > 2000:
             continue
         ok += 1
         assert close(out["U"][b], tight["U"]), (b, np.abs(out["U"][b] - tight["U"]).max())
@@ -179,12 +184,14 @@ def test_feasibility_and_masks_all_gaits():
     F = out["U"].reshape(pb.B, 10, 4, 3)
     st = pb.stance.astype(bool)
     assert np.all(F[~st] == 0.0)
-    fz = F[..., 2][st]
-    mu = np.broadcast_to(pb.mu[:, None, None], st.shape)[st]
-    tol = 0.15      # eps_rel * |z| with |z| up to 100 N
-    assert fz.min() >= 3.0 - tol and fz.max() <= 100.0 + tol
-    assert np.all(np.abs(F[..., 0][st]) <= mu * fz + tol)
-    assert np.all(np.abs(F[..., 1][st]) <= mu * fz + tol)
+    mu = np.broadcast_to(pb.mu[:, None, None], st.shape)
+    # OSQP primal tolerance of each problem: eps_abs + eps_rel * max(|Ax|, |z|)
+    Ax_max = (np.abs(F[..., :2]).max(-1) + mu * np.abs(F[..., 2])).reshape(pb.B, -1).max(1)
+    tol = (1e-3 + 1e-3 * np.maximum(Ax_max, 100.0))[:, None, None] * 1.05 + 1e-4
+    fz = F[..., 2]
+    assert np.all((fz >= 3.0 - tol)[st]) and np.all((fz <= 100.0 + tol)[st])
+    assert np.all((np.abs(F[..., 0]) <= mu * fz + tol)[st])
+    assert np.all((np.abs(F[..., 1]) <= mu * fz + tol)[st])
     # flight stages exist in the pronk problems and are all-zero
     assert (pb.stance.sum(-1) == 0).any()
 

@@ -10,3 +10,4 @@ from ._capi import CmpcError                                    # noqa: F401
 from .solver import BatchedMPC, MPC, SolveStats                 # noqa: F401
 
 __version__ = "0.1.0"
+from . import sharding                                           # noqa: F401,E402

@@ -303,3 +303,104 @@ def test_full_size_properties_batch_4096():
                                     pb.mu[perm], pb.gait_id[perm], pb.tick[perm])
     out2 = gpu_solve(pb2, warm_mode=0)
     assert np.array_equal(out2["U"], out["U"][perm])
+
+
+# ------------------------------------------------------------------------------------------
+# Drop-in MPC class (reference src/mpc.py:8-318 interface) on the golden run's states
+# ------------------------------------------------------------------------------------------
+class _FakeLite3:
+    """Stands in for the reference's Lite3Controller.retrieve_state (src/main.py:286-350)."""
+
+    def __init__(self, gold):
+        self.gold, self.t = gold, 0
+
+    def retrieve_state(self):
+        s, f = self.gold["state"][self.t], self.gold["feet"][self.t]
+        d = {leg: {"pos": np.concatenate([np.zeros(3), f[l]]), "vel": np.zeros(6)}
+             for l, leg in enumerate(pkg.LEGS)}
+        d["TORSO"] = {"pos": s[0:3].copy(), "vel": s[6:9].copy()}
+        d["com"] = {"pos": s[3:6].copy(), "vel": s[9:12].copy()}
+        return d
+
+
+class _RefLikePlanner:
+    """Object with the reference FootstepPlanner's `.plan` layout (list of dicts)."""
+
+    def __init__(self, gp):
+        self.plan = [{"pos": {leg: gp.pos[s, l] for l, leg in enumerate(pkg.LEGS)},
+                      "ang": gp.ang[s], "ss_duration": gp.ss, "ds_duration": gp.ds,
+                      "feet_id": list(gp.feet_id[s])} for s in range(gp.n_steps)]
+
+
+class _Logger:
+    def __init__(self):
+        self.track, self.pred = [], []
+
+    def log_tracking_data(self, actual, des):
+        self.track.append((actual, des))
+
+    def log_mpc_predictions(self, x_log, x_des, forces_pred, t):
+        self.pred.append((t, x_log.shape, x_des.shape, forces_pred.shape))
+
+
+def test_mpc_dropin_on_golden_states(gold):
+    from oracle.replay import params_from_golden, initial_from_golden
+    params = params_from_golden(gold, N=10)
+    initial = initial_from_golden(gold)
+    gp = pkg.GaitPlan.from_initial(initial, params)
+    lite3, logger = _FakeLite3(gold), _Logger()
+    mpc = pkg.MPC(lite3=lite3, initial=initial, footstep_planner=_RefLikePlanner(gp), params=params)
+    warm = None
+    for t in list(range(0, 40)) + [80]:
+        lite3.t = t
+        if t == 80:      # jump: bring the reference accumulators where the real run had them
+            mpc.com_pos_start[:] = gold["desired"][80][3:6]
+            mpc.yaw_start = gold["desired"][80][2]
+            warm = None
+            mpc.solver.reset_warm()
+        forces = mpc.solve(t, logger)
+        assert set(forces) == set(pkg.LEGS) and all(f.shape == (3,) and f.dtype == np.float64
+                                                    for f in forces.values())
+        assert mpc.x.shape == (13, 1) and mpc.x_log.shape == (12, 11) and mpc.x_plot.shape == (3, 11)
+        assert mpc.u.shape == (12,) and mpc.u_plot.shape == (12, 10)
+        # desired state of this tick is the reference's, bit for bit (src/mpc.py:202-214,261-262)
+        assert np.array_equal(logger.track[-1][1], gold["desired"][t])
+        # same algorithm in fp64 with the reference's warm-start semantics
+        x0 = np.concatenate([gold["state"][t], [params["g"]]])
+        xd = logger.track[-1][1]
+        xdes = pkg.desired_trajectory(10, 0.01, initial["roll"], initial["pitch"], xd[2], xd[3:6],
+                                      *pkg.reference_velocity(gp, t, params), params["g"])
+        r, stance = pkg.assemble_tick(gp, t, 10, 0.01, x0, gold["feet"][t], xdes)
+        H, g, Sc, c0, idx = srbd_qp.condensed_qp(np.float32(x0).astype(float), np.float32(r).astype(float),
+                                                 stance, np.float32(xdes).astype(float), 0.01)
+        xw = None if warm is None else np.concatenate([warm[i, 3 * l:3 * l + 3] for (i, l) in idx])
+        ref = ca.admm(H, g, 1.0, rho=0.3, check_every=5, x=xw, adaptive_interval=25,
+                      adaptive_tolerance=3.0)
+        U = np.zeros((10, 12))
+        for s, (i, l) in enumerate(idx):
+            U[i, 3 * l:3 * l + 3] = ref["x"][3 * s:3 * s + 3]
+        assert ref["status"] == 1
+        assert abs(mpc.iters - ref["iters"]) <= 10
+        X = c0 + (Sc @ ref["x"]).reshape(11, 13).T
+        Jg, Jr = srbd_qp.objective(np.vstack([mpc.x_log, np.full((1, 11), params["g"])]), xdes), \
+            srbd_qp.objective(X, xdes)
+        assert abs(Jg / Jr - 1) < 5e-3
+        if mpc.iters == ref["iters"]:
+            assert np.abs(mpc.u_plot.T - U).max() < 0.05
+        warm = mpc.u_plot.T.copy()
+    assert len(logger.track) == 41 and [p[0] for p in logger.pred] == [0, 80]
+    assert logger.pred[0][1:] == ((12, 11), (12, 11), (4, 10))
+    # stance legs of tick 0 carry the robot: sum fz close to m*g
+    lite3.t = 0
+
+
+def test_mpc_dropin_raises_when_not_solved(gold):
+    """CasADi raises RuntimeError when OSQP does not report 'solved' (SURVEY.md 8b)."""
+    from oracle.replay import params_from_golden, initial_from_golden
+    params = params_from_golden(gold, N=10)
+    initial = initial_from_golden(gold)
+    gp = pkg.GaitPlan.from_initial(initial, params)
+    mpc = pkg.MPC(lite3=_FakeLite3(gold), initial=initial, footstep_planner=gp, params=params,
+                  max_iter=3)
+    with pytest.raises(RuntimeError):
+        mpc.solve(0, _Logger())

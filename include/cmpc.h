@@ -121,7 +121,7 @@ int cmpc_condense(cmpc_handle* h, int32_t B, const float* x0, const float* r,
 /* Warm-start state (src/mpc.py:270-271 `set_initial`): forget it for the slots whose
  * `slot_mask[i] != 0` (all slots if slot_mask == NULL; HOST pointer of max_batch bytes). */
 int cmpc_reset_warm(cmpc_handle* h, const uint8_t* slot_mask);
-/* Copy warm-start forces x [B,N,12] and duals y [B,N,4,5] of slots [slot0, slot0+B)
+/* Copy warm-start forces x [B,N,12] and duals y [B,N,4,3] of slots [slot0, slot0+B)
  * to / from DEVICE buffers (y may be NULL). */
 int cmpc_get_warm(cmpc_handle* h, int32_t B, int32_t slot0, float* x, float* y, void* stream);
 int cmpc_set_warm(cmpc_handle* h, int32_t B, int32_t slot0, const float* x, const float* y,

@@ -202,8 +202,8 @@ int cmpc_default_config(cmpc_config* cfg, int32_t N, int32_t max_batch) {
   cfg->refresh_every = 5;
   cfg->warm_mode = CMPC_WARM_PRIMAL;
   cfg->adaptive_rho_interval = 25;      // OSQP adapts rho too (adaptive_rho = 1 by default)
-  cfg->adaptive_rho_tolerance = 3.0f;
-  cfg->rho_min = 0.03f;                 // fp32 Woodbury form loses accuracy for rho << |H|
+  cfg->adaptive_rho_tolerance = 2.0f;
+  cfg->rho_min = 0.05f;                 // fp32 Woodbury form loses accuracy for rho << |H|
   cfg->rho_max = 30.0f;
   cfg->device = 0;
   return CMPC_OK;
@@ -218,7 +218,7 @@ int cmpc_create(const cmpc_config* cfg, cmpc_handle** out) {
   if (c.max_batch <= 0) return fail(CMPC_ERR_INVALID, "max_batch must be positive");
   if (!(c.dt > 0) || !(c.mass > 0) || !(c.rho > 0) || !(c.sigma >= 0) || !(c.alpha > 0 && c.alpha < 2))
     return fail(CMPC_ERR_INVALID, "dt, mass, rho must be > 0, sigma >= 0, 0 < alpha < 2");
-  if (!(c.f_min <= c.f_max)) return fail(CMPC_ERR_INVALID, "f_min > f_max");
+  if (!(c.f_min >= 0.f) || !(c.f_min <= c.f_max)) return fail(CMPC_ERR_INVALID, "0 <= f_min <= f_max required");
   if (c.max_iter < 0 || c.check_every <= 0 || c.refresh_every < 0)
     return fail(CMPC_ERR_INVALID, "max_iter >= 0, check_every > 0, refresh_every >= 0 required");
   if (c.warm_mode < 0 || c.warm_mode > 2) return fail(CMPC_ERR_INVALID, "bad warm_mode");
@@ -280,12 +280,12 @@ int cmpc_create(const cmpc_config* cfg, cmpc_handle** out) {
   if ((e = cudaMalloc(&h->d_Minv, mbytes)) != cudaSuccess ||
       (e = cudaMalloc(&h->d_Mg, mbytes)) != cudaSuccess ||
       (e = cudaMalloc(&h->d_warm_x, slots * 12 * N * sizeof(float))) != cudaSuccess ||
-      (e = cudaMalloc(&h->d_warm_y, slots * 20 * N * sizeof(float))) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_warm_y, slots * 12 * N * sizeof(float))) != cudaSuccess ||
       (e = cudaMalloc(&h->d_warm_valid, slots)) != cudaSuccess ||
       (e = cudaMemcpy(h->d_Minv, Mif.data(), mbytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemcpy(h->d_Mg, Mf.data(), mbytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemset(h->d_warm_x, 0, slots * 12 * N * sizeof(float))) != cudaSuccess ||
-      (e = cudaMemset(h->d_warm_y, 0, slots * 20 * N * sizeof(float))) != cudaSuccess ||
+      (e = cudaMemset(h->d_warm_y, 0, slots * 12 * N * sizeof(float))) != cudaSuccess ||
       (e = cudaMemset(h->d_warm_valid, 0, slots)) != cudaSuccess) {
     cmpc_destroy(h);
     return fail(CMPC_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
@@ -491,7 +491,7 @@ int cmpc_get_warm(cmpc_handle* h, int32_t B, int32_t slot0, float* x, float* y, 
   CUDA_TRY(cudaMemcpyAsync(x, h->d_warm_x + (size_t)slot0 * 12 * N, (size_t)B * 12 * N * 4,
                            cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   if (y)
-    CUDA_TRY(cudaMemcpyAsync(y, h->d_warm_y + (size_t)slot0 * 20 * N, (size_t)B * 20 * N * 4,
+    CUDA_TRY(cudaMemcpyAsync(y, h->d_warm_y + (size_t)slot0 * 12 * N, (size_t)B * 12 * N * 4,
                              cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return CMPC_OK;
 }
@@ -507,10 +507,10 @@ int cmpc_set_warm(cmpc_handle* h, int32_t B, int32_t slot0, const float* x, cons
   CUDA_TRY(cudaMemcpyAsync(h->d_warm_x + (size_t)slot0 * 12 * N, x, (size_t)B * 12 * N * 4,
                            cudaMemcpyDeviceToDevice, s));
   if (y)
-    CUDA_TRY(cudaMemcpyAsync(h->d_warm_y + (size_t)slot0 * 20 * N, y, (size_t)B * 20 * N * 4,
+    CUDA_TRY(cudaMemcpyAsync(h->d_warm_y + (size_t)slot0 * 12 * N, y, (size_t)B * 12 * N * 4,
                              cudaMemcpyDeviceToDevice, s));
   else
-    CUDA_TRY(cudaMemsetAsync(h->d_warm_y + (size_t)slot0 * 20 * N, 0, (size_t)B * 20 * N * 4, s));
+    CUDA_TRY(cudaMemsetAsync(h->d_warm_y + (size_t)slot0 * 12 * N, 0, (size_t)B * 12 * N * 4, s));
   CUDA_TRY(cudaMemsetAsync(h->d_warm_valid + slot0, 1, (size_t)B, s));
   return CMPC_OK;
 }

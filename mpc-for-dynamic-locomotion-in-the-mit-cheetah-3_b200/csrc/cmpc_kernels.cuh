@@ -8,15 +8,17 @@
 // cost depends on the forces u only through the 6N-vector of per-stage wrenches
 //     w = G u,   w_j = [ Rz I^-1 sum_l [r_jl]x f_jl ;  sum_l f_jl / m ]
 //     H = G' M G,  M = blockdiag over 6 axes of constant N x N Gram matrices (host, fp64).
-// OSQP-style ADMM needs K^-1 with K = H + sigma I + rho A'A; A'A is diagonal
-// (diag(2,2,1+4mu^2) per stance leg), so K = D + G' M G and by the matrix-inversion lemma
-//     K^-1 = D^-1 - D^-1 G' P^-1 G D^-1,    P = M^-1 + G D^-1 G'   (6N x 6N, SPD).
+// OSQP-style ADMM (x-update / relaxation / dual update of Stellato et al. 2020) with the
+// constraint copy z = u kept in the friction frustum C = {fz in [f_min,f_max], |fx|,|fy| <= mu fz}
+// by an exact Euclidean projection.  The x-update needs K^-1, K = H + (sigma + rho) I = d^-1 I + G'MG;
+// by the matrix-inversion lemma
+//     K^-1 = d I - d^2 G' P^-1 G,    P = M^-1 + d G G'   (6N x 6N, SPD).
 // One CTA per problem:
-//   * "leg threads"   (4N): one per leg-stage, keep that leg's x(3), z(5), y(5) in registers;
+//   * "leg threads"   (4N): one per leg-stage, keep that leg's x(3), z(3), y(3) in registers;
 //   * "wrench threads"(6N*SPLIT): own one row (slice) of P, invert it in registers with a
 //     symmetric Gauss-Jordan sweep whose pivot rows are broadcast through shared memory,
 //     then apply P^-1 once per ADMM iteration.
-// The iteration is written in residual-correction form (K d = -r_dual - rho A' r_prim,
+// The iteration is written in residual-correction form (K d = -r_dual - rho r_prim,
 // x += alpha d) so fp32 solve errors do not accumulate, and uses M G d = P^-1 s to keep the
 // wrench-space gradient v = M G x up to date without a second matrix-vector product.
 #pragma once
@@ -38,7 +40,7 @@ struct SolveParams {
   float* __restrict__ dua_res;
   int32_t* __restrict__ status;
   float* __restrict__ warm_x;         // [slots][N][12]
-  float* __restrict__ warm_y;         // [slots][N][4][5]
+  float* __restrict__ warm_y;         // [slots][N][4][3]
   uint8_t* __restrict__ warm_valid;   // [slots]
   const float* __restrict__ Minv;     // [6][N][N]
   const float* __restrict__ Mg;       // [6][N][N]
@@ -164,6 +166,7 @@ solve_kernel(const SolveParams p) {
   __shared__ __align__(16) float s_s[NWP];             // wrench-space rhs  s = G D^-1 b
   __shared__ __align__(16) float s_q[NWP];             // q = P^-1 s   (also: w, v scratch)
   __shared__ __align__(16) float s_h[NWP];             // linear term h
+  __shared__ __align__(16) float s_S[NWP];             // Jacobi scaling 1/sqrt(P_ii) of the sweep
   __shared__ float s_red[2][LWARPS][8];
   __shared__ int s_mask[N];
 
@@ -178,13 +181,13 @@ solve_kernel(const SolveParams p) {
   for (int i = tid; i < 13; i += THREADS) s_x0[i] = __ldg(p.x0 + (size_t)b * 13 + i);
   for (int i = tid; i < NX; i += THREADS) s_xd[i] = __ldg(p.x_des + (size_t)b * NX + i);
   for (int i = tid; i < N; i += THREADS) s_mask[i] = (int)__ldg(p.mask + (size_t)b * N + i);
-  for (int i = tid; i < NWP; i += THREADS) { s_s[i] = 0.f; s_q[i] = 0.f; s_h[i] = 0.f; }
+  for (int i = tid; i < NWP; i += THREADS) { s_s[i] = 0.f; s_q[i] = 0.f; s_h[i] = 0.f; s_S[i] = 0.f; }
   const float mu = __ldg(p.mu + b);
   // issue every other global load of this problem now so that their DRAM latencies overlap
   const bool is_leg = tid < NLEG;
   float r_in[3] = {0.f, 0.f, 0.f};
   float wx_in[3] = {0.f, 0.f, 0.f};
-  float wy_in[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float wy_in[3] = {0.f, 0.f, 0.f};
   const bool warm = p.warm_mode != 0 && p.warm_valid[slot] != 0;
   if (is_leg) {
     const float* rp = p.r + ((size_t)b * NLEG + tid) * 3;
@@ -193,9 +196,8 @@ solve_kernel(const SolveParams p) {
       const float* wx = p.warm_x + ((size_t)slot * NLEG + tid) * 3;
       wx_in[0] = wx[0]; wx_in[1] = wx[1]; wx_in[2] = wx[2];
       if (p.warm_mode == 2) {
-        const float* wy = p.warm_y + ((size_t)slot * NLEG + tid) * 5;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) wy_in[k] = wy[k];
+        const float* wy = p.warm_y + ((size_t)slot * NLEG + tid) * 3;
+        wy_in[0] = wy[0]; wy_in[1] = wy[1]; wy_in[2] = wy[2];
       }
     }
   }
@@ -212,7 +214,7 @@ solve_kernel(const SolveParams p) {
   const int lj = tid >> 2, ll = tid & 3;            // stage, leg of a leg thread
   bool stance = false;
   float Gh[3][3];
-  float dxy = 0.f, dz = 0.f;
+  float dinv = 0.f;                                  // d = 1/(sigma + 2 r_weight + rho), 0 on swing legs
 #pragma unroll
   for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -241,35 +243,39 @@ solve_kernel(const SolveParams p) {
   // ---- phases 2+3 as a re-runnable step (adaptive rho refactorises) ------------------------
   float row[COLS];
   auto factorize = [&]() {
-  // D^-1 of this leg for the current rho (A'A = diag(2, 2, 1 + 4 mu^2) per stance leg)
-  dxy = stance ? 1.f / (p.sigma + 2.f * p.r_weight + 2.f * rho) : 0.f;
-  dz = stance ? 1.f / (p.sigma + 2.f * p.r_weight + rho * (1.f + 4.f * mu * mu)) : 0.f;
-  if (is_leg) {
-    s_G[tid][9] = dxy;
-    s_G[tid][10] = dz;
-  }
+  // d of this leg for the current rho (K = H + (sigma + rho) I on the stance forces)
+  dinv = stance ? 1.f / (p.sigma + 2.f * p.r_weight + rho) : 0.f;
+  if (is_leg) s_G[tid][9] = dinv;
   __syncthreads();
   // ---- phase 2: P = M^-1 + E (row slices in registers) ------------------------------------
 #pragma unroll
   for (int c = 0; c < COLS; ++c) row[c] = 0.f;
-  if (is_row) {
-    // E_j[ra][a'] = sum_l sum_c Gp[ra][c] d_c Gp[a'][c],  Gp = [Ghat ; I/m]
-    float E[6];
+  // E_j[ra][a'] = sum_l sum_c Gp[ra][c] d Gp[a'][c],  Gp = [Ghat ; I/m]
+  float E[6];
 #pragma unroll
-    for (int a2 = 0; a2 < 6; ++a2) E[a2] = 0.f;
+  for (int a2 = 0; a2 < 6; ++a2) E[a2] = 0.f;
+  const float* mi = p.Minv + ((size_t)(is_row ? ra : 0) * N + (is_row ? rj : 0)) * N;
+  float sc_i = 1.f;
+  if (is_row) {
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
       const float* g = s_G[4 * rj + l];
-      const float d[3] = {g[9], g[9], g[10]};
+      const float d = g[9];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float mine = (ra < 3 ? g[3 * ra + c] : (ra - 3 == c ? im : 0.f)) * d[c];
+        const float mine = (ra < 3 ? g[3 * ra + c] : (ra - 3 == c ? im : 0.f)) * d;
 #pragma unroll
         for (int a2 = 0; a2 < 3; ++a2) E[a2] += mine * g[3 * a2 + c];
         E[3 + c] += mine * im;
       }
     }
-    const float* mi = p.Minv + ((size_t)ra * N + rj) * N;
+    // Jacobi scaling: the sweep runs on S P S (unit diagonal, pivots <= 1); its fused special
+    // cases lose log2(pivot) bits when pivots are >> 1
+    sc_i = rsqrtf(__ldg(mi + rj) + E[ra]);
+    if (rs == 0) s_S[ri] = sc_i;
+  }
+  __syncthreads();
+  if (is_row) {
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
       const int col = rs * COLS + c;
@@ -278,6 +284,7 @@ solve_kernel(const SolveParams p) {
       if (col < NW) {
         if (a2 == ra) v = __ldg(mi + j2);
         if (j2 == rj) v += E[a2];
+        v *= sc_i * s_S[col];
       }
       row[c] = v;
     }
@@ -324,32 +331,54 @@ solve_kernel(const SolveParams p) {
       }
     }
   }
+  if (is_row) {
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      const int col = rs * COLS + c;
+      row[c] *= sc_i * (col < NW ? s_S[col] : 0.f);
+    }
+  }
   __syncthreads();
   };
   factorize();
 
   // ---- phase 4: initial iterate -----------------------------------------------------------
+  const float fmin = p.f_min, fmax = p.f_max;
+  const float inv1 = 1.f / (1.f + mu * mu), inv2 = 1.f / (1.f + 2.f * mu * mu);
+  // exact projection onto the friction frustum: minimise over fz the 1-D convex residual
+  // (fx, fy are clamped to +-mu fz), three linear pieces, then clamp fz to [f_min, f_max]
+  auto project = [&](float wx, float wy, float wz, float& zx, float& zy, float& zz) {
+    const float ax = fabsf(wx), ay = fabsf(wy);
+    const float big = fmaxf(ax, ay), small = fminf(ax, ay);
+    const float f2 = (wz + mu * big) * inv1;
+    const float f1 = (wz + mu * (ax + ay)) * inv2;
+    float fz = (mu * wz >= big) ? wz : ((mu * f2 >= small) ? f2 : f1);
+    fz = fminf(fmaxf(fz, fmin), fmax);
+    const float lim = mu * fz;
+    zx = fminf(fmaxf(wx, -lim), lim);
+    zy = fminf(fmaxf(wy, -lim), lim);
+    zz = fz;
+  };
   float x[3] = {0.f, 0.f, 0.f};
-  float y[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  float z[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float y[3] = {0.f, 0.f, 0.f};
+  float z[3] = {0.f, 0.f, 0.f};
   float gl[3] = {0.f, 0.f, 0.f};          // linear term of this leg:  G' h
-  float vj[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // wrench-space gradient v = M G x of this stage
+  float hj[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // h of this stage
+  float vh[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // v + h,  v = M G x  (wrench-space gradient)
   if (is_leg && stance) {
-    const float* hj = s_h + 6 * lj;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) hj[a] = s_h[6 * lj + a];
 #pragma unroll
     for (int k = 0; k < 3; ++k)
       gl[k] = Gh[0][k] * hj[0] + Gh[1][k] * hj[1] + Gh[2][k] * hj[2] + im * hj[3 + k];
     if (warm) {
       x[0] = wx_in[0]; x[1] = wx_in[1]; x[2] = wx_in[2];
-#pragma unroll
-      for (int k = 0; k < 5; ++k) y[k] = wy_in[k];
+      y[0] = wy_in[0]; y[1] = wy_in[1]; y[2] = wy_in[2];
     }
-    z[0] = fminf(fmaxf(x[2], p.f_min), p.f_max);
-    z[1] = fminf(x[0] - mu * x[2], 0.f);
-    z[2] = fminf(-x[0] - mu * x[2], 0.f);
-    z[3] = fminf(x[1] - mu * x[2], 0.f);
-    z[4] = fminf(-x[1] - mu * x[2], 0.f);
+    project(x[0], x[1], x[2], z[0], z[1], z[2]);
   }
+#pragma unroll
+  for (int a = 0; a < 6; ++a) vh[a] = hj[a];
 
   // exact wrench-space gradient  v = M (G x)  (uniform: every thread takes part)
   auto refresh_gradient = [&]() {
@@ -372,9 +401,9 @@ solve_kernel(const SolveParams p) {
       s_q[ri] = acc;
     }
     __syncthreads();
-    if (is_leg) {
+    if (is_leg && stance) {
 #pragma unroll
-      for (int a = 0; a < 6; ++a) vj[a] = s_q[6 * lj + a];
+      for (int a = 0; a < 6; ++a) vh[a] = s_q[6 * lj + a] + hj[a];
     }
     __syncthreads();
   };
@@ -397,52 +426,34 @@ solve_kernel(const SolveParams p) {
   // ---- phase 5: ADMM ------------------------------------------------------------------------
   int it = 0;
   int status = 0;
+  float pri = 0.f, dua = 0.f;
+  const float two_rw = 2.f * p.r_weight;
   int rho_updates = 0;
   int next_chk = 0;
   int next_ref = p.refresh_every > 0 ? p.refresh_every : -1;
   int next_adp = p.adaptive_rho_interval > 0 ? p.adaptive_rho_interval : -1;
-  float pri = 0.f, dua = 0.f;
-  const float two_rw = 2.f * p.r_weight;
   for (;;) {
     if (it == next_ref) {
       next_ref += p.refresh_every;
       refresh_gradient();
     }
-    // leg phase A: residuals of the current iterate, rhs of the correction equation
-    float t[3] = {0.f, 0.f, 0.f};
     const bool adapt_now = it == next_adp;
     if (adapt_now) next_adp += p.adaptive_rho_interval;
     const bool chk = it == next_chk || it >= p.max_iter || adapt_now;
     if (it == next_chk) next_chk += p.check_every;
-    float st_[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // leg phase A: residuals of the current iterate, rhs of the correction equation
+    float t[3] = {0.f, 0.f, 0.f};
+    float st_[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     if (leg_warp) {   // whole warps (all-zero state on non-leg lanes) so the shuffles are convergent
-      float Ax[5], Aty[3], Hx[3], rd[3], rp[5];
-      Ax[0] = x[2];
-      Ax[1] = x[0] - mu * x[2];
-      Ax[2] = -x[0] - mu * x[2];
-      Ax[3] = x[1] - mu * x[2];
-      Ax[4] = -x[1] - mu * x[2];
-      Aty[0] = y[1] - y[2];
-      Aty[1] = y[3] - y[4];
-      Aty[2] = y[0] - mu * (y[1] + y[2] + y[3] + y[4]);
+      float gr[3], rp[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        Hx[k] = Gh[0][k] * vj[0] + Gh[1][k] * vj[1] + Gh[2][k] * vj[2] + im * vj[3 + k] + two_rw * x[k];
-        rd[k] = Hx[k] + gl[k] + Aty[k];
+        // (H x + g)_k = G'(v + h) + 2 r_weight x
+        gr[k] = Gh[0][k] * vh[0] + Gh[1][k] * vh[1] + Gh[2][k] * vh[2] + im * vh[3 + k] + two_rw * x[k];
+        rp[k] = x[k] - z[k];
+        // K dlt = -(Hx + g + y) - rho (x - z)
+        t[k] = -dinv * (gr[k] + y[k] + rho * rp[k]);
       }
-#pragma unroll
-      for (int k = 0; k < 5; ++k) rp[k] = Ax[k] - z[k];
-      if (!stance) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { Hx[k] = 0.f; rd[k] = 0.f; }
-      }
-      // b = -rd - rho A' rp ; t = D^-1 b
-      const float b0 = -rd[0] - rho * (rp[1] - rp[2]);
-      const float b1 = -rd[1] - rho * (rp[3] - rp[4]);
-      const float b2 = -rd[2] - rho * (rp[0] - mu * (rp[1] + rp[2] + rp[3] + rp[4]));
-      t[0] = dxy * b0;
-      t[1] = dxy * b1;
-      t[2] = dz * b2;
       float sv[6];
 #pragma unroll
       for (int a = 0; a < 3; ++a)
@@ -452,43 +463,37 @@ solve_kernel(const SolveParams p) {
       if (is_leg && ll < 3)
         *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = make_float2(sv[2 * ll], sv[2 * ll + 1]);
       if (chk) {
-        float m;
-        m = 0.f;
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, sum = 0.f;
+        if (stance) {
 #pragma unroll
-        for (int k = 0; k < 5; ++k) m = fmaxf(m, fabsf(rp[k]));
-        st_[0] = m;                                            // primal residual
-        st_[1] = fmaxf(fabsf(rd[0]), fmaxf(fabsf(rd[1]), fabsf(rd[2])));   // dual residual
-        m = 0.f;
+          for (int k = 0; k < 3; ++k) {
+            const float rd = gr[k] + y[k];
+            m0 = fmaxf(m0, fabsf(rp[k]));                                   // primal residual
+            m1 = fmaxf(m1, fabsf(rd));                                      // dual residual
+            m2 = fmaxf(m2, fmaxf(fabsf(x[k]), fabsf(z[k])));                // max(|x|,|z|)
+            m3 = fmaxf(m3, fmaxf(fabsf(gr[k] - gl[k]), fabsf(y[k])));       // max(|Hx|,|y|)
+            sum += x[k] + rd;
+          }
+        }
+        st_[0] = m0; st_[1] = m1; st_[2] = m2; st_[3] = m3;
+        st_[4] = fabsf(sum * 0.f);      // NaN / Inf guard: any non-finite value makes this NaN
 #pragma unroll
-        for (int k = 0; k < 5; ++k) m = fmaxf(m, fmaxf(fabsf(Ax[k]), fabsf(z[k])));
-        st_[2] = m;                                            // max(|Ax|,|z|)
-        m = 0.f;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) m = fmaxf(m, fmaxf(fabsf(Hx[k]), fabsf(Aty[k])));
-        st_[3] = m;                                            // max(|Hx|,|A'y|)
-        // NaN / Inf guard: any non-finite value makes the product NaN
-        st_[4] = fabsf((x[0] + x[1] + x[2] + rd[0] + rd[1] + rd[2]) * 0.f);
-      }
-    }
-    if (chk && leg_warp) {
-      const int pb = 0;
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const float m = warp_max_nonneg(st_[k]);
-        if (lane == 0) s_red[pb][warp][k] = m;
+        for (int k = 0; k < 5; ++k) {
+          const float m = warp_max_nonneg(st_[k]);
+          if (lane == 0) s_red[0][warp][k] = m;
+        }
       }
     }
     __syncthreads();
     if (chk) {
-      const int pb = 0;
       float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, m4 = 0.f;
 #pragma unroll
       for (int wv = 0; wv < LWARPS; ++wv) {
-        m0 = fmaxf(m0, s_red[pb][wv][0]);
-        m1 = fmaxf(m1, s_red[pb][wv][1]);
-        m2 = fmaxf(m2, s_red[pb][wv][2]);
-        m3 = fmaxf(m3, s_red[pb][wv][3]);
-        m4 += s_red[pb][wv][4];
+        m0 = fmaxf(m0, s_red[0][wv][0]);
+        m1 = fmaxf(m1, s_red[0][wv][1]);
+        m2 = fmaxf(m2, s_red[0][wv][2]);
+        m3 = fmaxf(m3, s_red[0][wv][3]);
+        m4 += s_red[0][wv][4];
       }
       pri = m0;
       dua = m1;
@@ -533,38 +538,29 @@ solve_kernel(const SolveParams p) {
       if (is_row && rs == 0) s_q[ri] = -acc;
     }
     __syncthreads();
-    // leg phase B: x += alpha d, relaxed projection, dual update
+    // leg phase B: x-update, relaxed projection, dual update
     if (is_leg && stance) {
-      const float* q = s_q + 6 * lj;
       float qv[6];
 #pragma unroll
-      for (int a = 0; a < 6; ++a) qv[a] = q[a];
-      float d[3];
-      d[0] = t[0] - dxy * (Gh[0][0] * qv[0] + Gh[1][0] * qv[1] + Gh[2][0] * qv[2] + im * qv[3]);
-      d[1] = t[1] - dxy * (Gh[0][1] * qv[0] + Gh[1][1] * qv[1] + Gh[2][1] * qv[2] + im * qv[4]);
-      d[2] = t[2] - dz * (Gh[0][2] * qv[0] + Gh[1][2] * qv[1] + Gh[2][2] * qv[2] + im * qv[5]);
+      for (int a = 0; a < 6; ++a) qv[a] = s_q[6 * lj + a];
 #pragma unroll
-      for (int a = 0; a < 6; ++a) vj[a] = fmaf(alpha, qv[a], vj[a]);
-      const float xt0 = x[0] + d[0], xt1 = x[1] + d[1], xt2 = x[2] + d[2];
-      float zt[5];
-      zt[0] = xt2;
-      zt[1] = xt0 - mu * xt2;
-      zt[2] = -xt0 - mu * xt2;
-      zt[3] = xt1 - mu * xt2;
-      zt[4] = -xt1 - mu * xt2;
+      for (int a = 0; a < 6; ++a) vh[a] = fmaf(alpha, qv[a], vh[a]);
+      float w3[3];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) x[k] = fmaf(alpha, d[k], x[k]);
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const float zh = alpha * zt[k] + (1.f - alpha) * z[k];
-        float zn = zh + y[k] * rho_inv;
-        zn = (k == 0) ? fminf(fmaxf(zn, p.f_min), p.f_max) : fminf(zn, 0.f);
-        y[k] = fmaf(rho, zh - zn, y[k]);
-        z[k] = zn;
+      for (int k = 0; k < 3; ++k) {
+        const float dl = t[k] - dinv * (Gh[0][k] * qv[0] + Gh[1][k] * qv[1] + Gh[2][k] * qv[2] + im * qv[3 + k]);
+        const float xt = x[k] + dl;
+        x[k] = fmaf(alpha, dl, x[k]);      // OSQP: x <- alpha x~ + (1 - alpha) x
+        const float zh = alpha * xt + (1.f - alpha) * z[k];
+        w3[k] = fmaf(y[k], rho_inv, zh);
       }
+      project(w3[0], w3[1], w3[2], z[0], z[1], z[2]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) y[k] = rho * (w3[k] - z[k]);
     }
     ++it;
   }
+  (void)rho_updates;
 
   // ---- phase 6: outputs -----------------------------------------------------------------------
   if (is_leg) {
@@ -572,9 +568,8 @@ solve_kernel(const SolveParams p) {
     up[0] = x[0]; up[1] = x[1]; up[2] = x[2];
     float* wx = p.warm_x + ((size_t)slot * NLEG + tid) * 3;
     wx[0] = x[0]; wx[1] = x[1]; wx[2] = x[2];
-    float* wy = p.warm_y + ((size_t)slot * NLEG + tid) * 5;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) wy[k] = y[k];
+    float* wy = p.warm_y + ((size_t)slot * NLEG + tid) * 3;
+    wy[0] = y[0]; wy[1] = y[1]; wy[2] = y[2];
   }
   if (tid == 0) {
     if (p.iters) p.iters[b] = it;

@@ -162,7 +162,7 @@ class BatchedMPC:
         import torch
         dev = torch.device("cuda", self.device)
         x = torch.empty((B, self.N, 12), dtype=torch.float32, device=dev)
-        y = torch.empty((B, self.N, 4, 5), dtype=torch.float32, device=dev)
+        y = torch.empty((B, self.N, 4, 3), dtype=torch.float32, device=dev)
         s = torch.cuda.current_stream(dev).cuda_stream
         _capi.check(_capi.lib().cmpc_get_warm(self._h, B, slot0, _ptr(x), _ptr(y), C.c_void_p(s)))
         return x, y

@@ -32,15 +32,12 @@ for refresh in (1, 2, 5, 10, 25, 0):
 
 pb = synthetic_batch(4096, N=10, seed=0)
 args = [torch.from_numpy(a).cuda() for a in pb.f32()]
-for name, opts in [("v0 default", dict()), ("v1 split2", dict(kernel_variant=1)), ("v2 split4", dict(kernel_variant=2)),
-                   ("v0 tol5", dict(adaptive_rho_tolerance=5.0)), ("v0 refresh25", dict(refresh_every=25)),
-                   ("v0 check10", dict(check_every=10)),
-                   ("v0 K=50 fixed", dict(adaptive_rho_interval=0, max_iter=50, check_every=100000, eps_abs=0., eps_rel=0.)),
-                   ("v1 K=50 fixed", dict(kernel_variant=1, adaptive_rho_interval=0, max_iter=50, check_every=100000, eps_abs=0., eps_rel=0.)),
-                   ("v2 K=50 fixed", dict(kernel_variant=2, adaptive_rho_interval=0, max_iter=50, check_every=100000, eps_abs=0., eps_rel=0.)),
-                   ("v0 K=0", dict(adaptive_rho_interval=0, max_iter=0, check_every=100000, eps_abs=0., eps_rel=0.)),
-                   ("v1 K=0", dict(kernel_variant=1, adaptive_rho_interval=0, max_iter=0, check_every=100000, eps_abs=0., eps_rel=0.)),
-                   ("v2 K=0", dict(kernel_variant=2, adaptive_rho_interval=0, max_iter=0, check_every=100000, eps_abs=0., eps_rel=0.))]:
+for name, opts in [("default", dict()), ("tol3", dict(adaptive_rho_tolerance=3.0)), ("adapt15", dict(adaptive_rho_interval=15)),
+                   ("rho .5", dict(rho=0.5)), ("rho .2", dict(rho=0.2)), ("alpha 1.7", dict(alpha=1.7)), ("alpha 1.5", dict(alpha=1.5)),
+                   ("refresh 10", dict(refresh_every=10)), ("check 1", dict(check_every=1)), ("check 2", dict(check_every=2)), ("check 10", dict(check_every=10)),
+                   ("no adapt", dict(adaptive_rho_interval=0)),
+                   ("K=25 fixed", dict(adaptive_rho_interval=0, max_iter=25, check_every=100000, eps_abs=0., eps_rel=0.)),
+                   ("K=0", dict(adaptive_rho_interval=0, max_iter=0, check_every=100000, eps_abs=0., eps_rel=0.))]:
     mpc = pkg.BatchedMPC(N=10, max_batch=4096, warm_mode=0, **opts)
     out = mpc.alloc_outputs(4096)
     ms = timeit(mpc, args, out)
@@ -48,7 +45,7 @@ for name, opts in [("v0 default", dict()), ("v1 split2", dict(kernel_variant=1))
     print(f"{name:20s}: {ms:.3f} ms/batch  {4096/ms*1e3/1e6:.2f} M solves/s  iters mean {it.mean():.1f} p99 {np.percentile(it,99):.0f} max {it.max()}  solved {np.mean(stt==1):.4f} nan {np.mean(stt==-1):.4f}", flush=True)
 # lone-CTA latency: B=1, fixed K
 one = [t[:1].contiguous() for t in args]
-for v in (0, 1, 2):
+for v in (0,):
     res = []
     for K in (0, 100, 1000):
         mpc = pkg.BatchedMPC(N=10, max_batch=1, warm_mode=0, kernel_variant=v, adaptive_rho_interval=0, max_iter=K, check_every=5, eps_abs=0., eps_rel=0.)

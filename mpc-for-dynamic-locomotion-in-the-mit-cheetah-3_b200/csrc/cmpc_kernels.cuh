@@ -291,6 +291,19 @@ solve_kernel(const SolveParams p) {
   }
 
   // ---- phase 3: symmetric Gauss-Jordan sweep, rows in registers -> row = -P^-1 ------------
+  // Step k: the owner of row k publishes it through shared memory with entry k replaced by
+  // a_kk - 1, plus d = 1/a_kk.  EVERY thread then runs the same FMA stream
+  //     row[c] += nf * p'[c],   nf = -a_ik d  (other rows),   nf = d - 1  (the pivot row itself)
+  // which yields a_ic - a_ik a_kc / a_kk, a_ik / a_kk in column k, and d * p' for the pivot row.
+  // Only the pivot row's own diagonal comes out as 2 - d instead of -d; the true diagonal of
+  // every row is therefore tracked in a register (`diag`, also the next pivot) and the constant
+  // +2 on the in-row copy is removed once at the end.  No divergent special-case path, no
+  // dynamic register indexing.
+  float diag = 1.f, rdiag = 1.f;
+  if (is_row) {
+    diag = (__ldg(mi + rj) + E[ra]) * sc_i * sc_i;
+    rdiag = __fdividef(1.f, diag);
+  }
   for (int k = 0; k < NW; ++k) {
     float* buf = s_row[k & 1];
     if (is_row && ri == k) {
@@ -298,44 +311,36 @@ solve_kernel(const SolveParams p) {
       for (int c = 0; c < COLS; c += 4)
         *reinterpret_cast<float4*>(buf + rs * COLS + c) =
             make_float4(row[c], row[c + 1], row[c + 2], row[c + 3]);
-      if (k / COLS == rs) {   // this slice holds the pivot: publish 1/pivot, patch entry k
-        const float akk = buf[k];
-        buf[k] = akk - 1.f;
-        buf[NWP] = 1.f / akk;
+      if (k / COLS == rs) {   // this slice holds the pivot (stores of one thread stay ordered)
+        buf[k] = diag - 1.f;
+        buf[NWP] = rdiag;
       }
     }
     __syncthreads();
     if (is_row) {
       const float d = buf[NWP];
+      const float m = buf[ri];
+      const bool own = ri == k;
+      const float nf = own ? d - 1.f : -m * d;
+      diag = own ? -d : fmaf(nf, m, diag);
+      rdiag = __fdividef(1.f, diag);
       const float* pr = buf + rs * COLS;
-      if (ri == k) {
-        const float nf = 1.f + d;     // row = -row + (1+d) p'
 #pragma unroll
-        for (int c = 0; c < COLS; c += 4) {
-          const float4 pv = *reinterpret_cast<const float4*>(pr + c);
-          row[c] = fmaf(nf, pv.x, -row[c]);
-          row[c + 1] = fmaf(nf, pv.y, -row[c + 1]);
-          row[c + 2] = fmaf(nf, pv.z, -row[c + 2]);
-          row[c + 3] = fmaf(nf, pv.w, -row[c + 3]);
-        }
-      } else {
-        const float nf = -buf[ri] * d;  // row -= (a_ik d) p'
-#pragma unroll
-        for (int c = 0; c < COLS; c += 4) {
-          const float4 pv = *reinterpret_cast<const float4*>(pr + c);
-          row[c] = fmaf(nf, pv.x, row[c]);
-          row[c + 1] = fmaf(nf, pv.y, row[c + 1]);
-          row[c + 2] = fmaf(nf, pv.z, row[c + 2]);
-          row[c + 3] = fmaf(nf, pv.w, row[c + 3]);
-        }
+      for (int c = 0; c < COLS; c += 4) {
+        const float4 pv = *reinterpret_cast<const float4*>(pr + c);
+        row[c] = fmaf(nf, pv.x, row[c]);
+        row[c + 1] = fmaf(nf, pv.y, row[c + 1]);
+        row[c + 2] = fmaf(nf, pv.z, row[c + 2]);
+        row[c + 3] = fmaf(nf, pv.w, row[c + 3]);
       }
     }
   }
-  if (is_row) {
+  if (is_row) {   // remove the +2 of the in-row diagonal copy, undo the Jacobi scaling
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
       const int col = rs * COLS + c;
-      row[c] *= sc_i * (col < NW ? s_S[col] : 0.f);
+      const float v = col == ri ? diag : row[c];
+      row[c] = v * sc_i * (col < NW ? s_S[col] : 0.f);
     }
   }
   __syncthreads();

@@ -82,6 +82,8 @@ typedef struct cmpc_config {
   float rho_min, rho_max;        /* clamp of the adapted rho                                 */
   int32_t kernel_variant; /* 0 = default thread layout; >0 selects an alternative (more threads
                              per problem) where one is compiled, see DESIGN.md            */
+  int32_t lpt_schedule; /* >0: batches of at least this size are launched hardest-first
+                           (conditioning score), 0 = launch in batch order               */
   int32_t device;       /* CUDA device ordinal                                       */
 } cmpc_config;
 

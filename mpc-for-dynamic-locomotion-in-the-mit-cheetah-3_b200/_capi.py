@@ -42,7 +42,8 @@ class Config(C.Structure):
                 ("refresh_every", C.c_int32), ("warm_mode", C.c_int32),
                 ("adaptive_rho_interval", C.c_int32), ("adaptive_rho_tolerance", C.c_float),
                 ("rho_min", C.c_float), ("rho_max", C.c_float),
-                ("kernel_variant", C.c_int32), ("device", C.c_int32)]
+                ("kernel_variant", C.c_int32), ("lpt_schedule", C.c_int32),
+                ("device", C.c_int32)]
 
 
 def needs_build() -> bool:

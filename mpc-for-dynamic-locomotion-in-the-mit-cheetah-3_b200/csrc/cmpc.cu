@@ -71,6 +71,9 @@ struct cmpc_handle {
   float* d_warm_x = nullptr;
   float* d_warm_y = nullptr;
   uint8_t* d_warm_valid = nullptr;
+  float* d_score = nullptr;      // LPT scheduling scratch
+  int32_t* d_order = nullptr;
+  int32_t* d_hist = nullptr;
   Staging st;
   std::atomic<int64_t> launches{0};
 };
@@ -79,10 +82,16 @@ namespace {
 
 using SolveLaunch = cudaError_t (*)(const cmpc::SolveParams&, cudaStream_t);
 using CondenseLaunch = cudaError_t (*)(const cmpc::CondenseParams&, cudaStream_t);
+using ScoreLaunch = cudaError_t (*)(const cmpc::ScoreParams&, cudaStream_t);
 
 template <int N, int SPLIT, int MINB>
 cudaError_t launch_solve(const cmpc::SolveParams& p, cudaStream_t s) {
   cmpc::solve_kernel<N, SPLIT, MINB><<<p.B, cmpc::Geo<N, SPLIT>::THREADS, 0, s>>>(p);
+  return cudaGetLastError();
+}
+template <int N>
+cudaError_t launch_score(const cmpc::ScoreParams& p, cudaStream_t s) {
+  cmpc::score_kernel<N><<<(p.B + 127) / 128, 128, 0, s>>>(p);
   return cudaGetLastError();
 }
 template <int N>
@@ -95,19 +104,20 @@ struct HorizonEntry {
   int N;
   SolveLaunch solve[3];      // thread-layout variants (nullptr = not compiled)
   CondenseLaunch condense;
+  ScoreLaunch score;
 };
 
 // Horizons with compiled kernels.  <N, SPLIT, MINB>: SPLIT threads share one row of the
 // 6N x 6N wrench matrix so that the register-resident row slice stays <= 60 floats.
 const HorizonEntry kHorizons[] = {
-    {4, {launch_solve<4, 1, 8>, nullptr, nullptr}, launch_condense<4>},
-    {5, {launch_solve<5, 1, 8>, nullptr, nullptr}, launch_condense<5>},
-    {8, {launch_solve<8, 1, 8>, nullptr, nullptr}, launch_condense<8>},
-    {10, {launch_solve<10, 1, 8>, launch_solve<10, 2, 4>, launch_solve<10, 4, 2>}, launch_condense<10>},
-    {12, {launch_solve<12, 2, 4>, nullptr, nullptr}, launch_condense<12>},
-    {16, {launch_solve<16, 2, 3>, nullptr, nullptr}, launch_condense<16>},
-    {20, {launch_solve<20, 2, 2>, nullptr, nullptr}, launch_condense<20>},
-    {30, {launch_solve<30, 4, 1>, nullptr, nullptr}, launch_condense<30>},
+    {4, {launch_solve<4, 1, 8>, nullptr, nullptr}, launch_condense<4>, launch_score<4>},
+    {5, {launch_solve<5, 1, 8>, nullptr, nullptr}, launch_condense<5>, launch_score<5>},
+    {8, {launch_solve<8, 1, 8>, nullptr, nullptr}, launch_condense<8>, launch_score<8>},
+    {10, {launch_solve<10, 1, 8>, launch_solve<10, 2, 4>, launch_solve<10, 4, 2>}, launch_condense<10>, launch_score<10>},
+    {12, {launch_solve<12, 2, 4>, nullptr, nullptr}, launch_condense<12>, launch_score<12>},
+    {16, {launch_solve<16, 2, 3>, nullptr, nullptr}, launch_condense<16>, launch_score<16>},
+    {20, {launch_solve<20, 2, 2>, nullptr, nullptr}, launch_condense<20>, launch_score<20>},
+    {30, {launch_solve<30, 4, 1>, nullptr, nullptr}, launch_condense<30>, launch_score<30>},
 };
 
 const HorizonEntry* find_horizon(int N) {
@@ -149,6 +159,27 @@ void fill_solve_params(const cmpc_handle* h, cmpc::SolveParams& p) {
   p.adaptive_rho_tolerance = c.adaptive_rho_tolerance;
   p.rho_min = c.rho_min;
   p.rho_max = c.rho_max;
+}
+
+// Enqueue the LPT ordering of a batch (2 small kernels) and point p.order at it.
+// `order_off` lets the host path order several chunks independently.
+int schedule_batch(cmpc_handle* h, cmpc::SolveParams& p, int order_off, cudaStream_t s) {
+  p.order = nullptr;
+  if (!h->cfg.lpt_schedule || p.B < h->cfg.lpt_schedule) return CMPC_OK;
+  const cmpc_config& c = h->cfg;
+  cmpc::ScoreParams sp{};
+  sp.x0 = p.x0; sp.r = p.r; sp.mask = p.mask; sp.Mg = h->d_Mg;
+  sp.score = h->d_score + order_off;
+  sp.hist = h->d_hist;
+  sp.B = p.B;
+  sp.inv_mass = 1.0f / c.mass;
+  for (int i = 0; i < 3; ++i) sp.ib[i] = c.ibody_inv[i];
+  CUDA_TRY(find_horizon(c.N)->score(sp, s));
+  cmpc::order_kernel<<<1, 1024, 0, s>>>(sp.score, h->d_hist, h->d_order + order_off, p.B);
+  CUDA_TRY(cudaGetLastError());
+  h->launches.fetch_add(2);
+  p.order = h->d_order + order_off;
+  return CMPC_OK;
 }
 
 int check_batch(const cmpc_handle* h, int B, int slot0) {
@@ -205,6 +236,7 @@ int cmpc_default_config(cmpc_config* cfg, int32_t N, int32_t max_batch) {
   cfg->adaptive_rho_tolerance = 2.0f;
   cfg->rho_min = 0.05f;                 // fp32 Woodbury form loses accuracy for rho << |H|
   cfg->rho_max = 30.0f;
+  cfg->lpt_schedule = 1024;             // hardest-first launch order for batches >= this size
   cfg->device = 0;
   return CMPC_OK;
 }
@@ -282,11 +314,15 @@ int cmpc_create(const cmpc_config* cfg, cmpc_handle** out) {
       (e = cudaMalloc(&h->d_warm_x, slots * 12 * N * sizeof(float))) != cudaSuccess ||
       (e = cudaMalloc(&h->d_warm_y, slots * 12 * N * sizeof(float))) != cudaSuccess ||
       (e = cudaMalloc(&h->d_warm_valid, slots)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_score, slots * sizeof(float))) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_order, slots * sizeof(int32_t))) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_hist, 64 * sizeof(int32_t))) != cudaSuccess ||
       (e = cudaMemcpy(h->d_Minv, Mif.data(), mbytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemcpy(h->d_Mg, Mf.data(), mbytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemset(h->d_warm_x, 0, slots * 12 * N * sizeof(float))) != cudaSuccess ||
       (e = cudaMemset(h->d_warm_y, 0, slots * 12 * N * sizeof(float))) != cudaSuccess ||
-      (e = cudaMemset(h->d_warm_valid, 0, slots)) != cudaSuccess) {
+      (e = cudaMemset(h->d_warm_valid, 0, slots)) != cudaSuccess ||
+      (e = cudaMemset(h->d_hist, 0, 64 * sizeof(int32_t))) != cudaSuccess) {
     cmpc_destroy(h);
     return fail(CMPC_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
   }
@@ -302,6 +338,9 @@ int cmpc_destroy(cmpc_handle* h) {
   cudaFree(h->d_warm_x);
   cudaFree(h->d_warm_y);
   cudaFree(h->d_warm_valid);
+  cudaFree(h->d_score);
+  cudaFree(h->d_order);
+  cudaFree(h->d_hist);
   if (h->st.h_in) cudaFreeHost(h->st.h_in);
   if (h->st.h_out) cudaFreeHost(h->st.h_out);
   cudaFree(h->st.d_in);
@@ -328,6 +367,8 @@ int cmpc_solve(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, const 
   p.U = U; p.X = X; p.iters = iters; p.pri_res = pri_res; p.dua_res = dua_res; p.status = status;
   p.B = B;
   p.slot0 = slot0;
+  rc = schedule_batch(h, p, 0, (cudaStream_t)stream);
+  if (rc) return rc;
   CUDA_TRY(pick_solve(h->cfg)(p, (cudaStream_t)stream));
   h->launches.fetch_add(1);
   return CMPC_OK;
@@ -446,6 +487,8 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, c
     p.status = (int32_t*)(dout + La.status);
     p.B = n;
     p.slot0 = slot0 + lo;
+    // chunks run on different streams but share the 64-bin histogram: order on one stream
+    p.order = nullptr;
     CUDA_TRY(solve_fn(p, s));
     h->launches.fetch_add(1);
     const size_t out_n = X ? La.out_total : La.X;

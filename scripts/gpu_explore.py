@@ -32,7 +32,7 @@ for refresh in (1, 2, 5, 10, 25, 0):
 
 pb = synthetic_batch(4096, N=10, seed=0)
 args = [torch.from_numpy(a).cuda() for a in pb.f32()]
-for name, opts in [("default", dict()), ("default again", dict()), ("refresh 2", dict(refresh_every=2)), ("rho .5", dict(rho=0.5)),
+for name, opts in [("default (lpt)", dict()), ("no lpt", dict(lpt_schedule=0)), ("lpt rho .5", dict(rho=0.5)), ("lpt tol3", dict(adaptive_rho_tolerance=3.0)),
                    ("K=25 fixed", dict(adaptive_rho_interval=0, max_iter=25, check_every=100000, eps_abs=0., eps_rel=0.)),
                    ("K=0", dict(adaptive_rho_interval=0, max_iter=0, check_every=100000, eps_abs=0., eps_rel=0.))]:
     mpc = pkg.BatchedMPC(N=10, max_batch=4096, warm_mode=0, **opts)

@@ -129,6 +129,38 @@ int cmpc_get_warm(cmpc_handle* h, int32_t B, int32_t slot0, float* x, float* y, 
 int cmpc_set_warm(cmpc_handle* h, int32_t B, int32_t slot0, const float* x, const float* y,
                   void* stream);
 
+/* ---- on-device parameter assembly and closed-loop plant ------------
+ * Per-robot gait tables, all DEVICE pointers: the arrays of reference FootstepPlanner.plan
+ * (src/footstep_planner.py:72-177) plus the reference velocities of src/main.py:31-46. */
+typedef struct cmpc_gait_tables {
+  const float* plan_pos;    /* [B,S,4,3] planned footholds per step                        */
+  const uint8_t* feet_id;   /* [B,S] stance bits of each step's single-support part        */
+  const int32_t* ss;        /* [B] single-support ticks                                    */
+  const int32_t* ds;        /* [B] double-support ticks                                    */
+  const float* v_ref;       /* [B,3]                                                       */
+  const float* omega_ref;   /* [B]                                                         */
+  const float* rp0;         /* [B,2] initial roll, pitch (src/mpc.py:203)                  */
+  int32_t S;                /* steps in the plan                                           */
+  int32_t total_steps;      /* params['total_steps'] (src/mpc.py:181)                      */
+  float step_height;        /* src/foot_trajectory_generator.py:23                         */
+  float g;                  /* params['g']                                                 */
+} cmpc_gait_tables;
+
+/* Replaces the Python parameter loops of MPC.solve (src/mpc.py:178-255) for B robots at the
+ * tick stored in `tick` (device int32): writes x_des [B,N+1,13], r [B,N,4,3], mask [B,N].
+ * x [B,13] measured state, yaw_start [B] / com_start [B,3] reference accumulators. */
+int cmpc_assemble(cmpc_handle* h, int32_t B, const cmpc_gait_tables* gt, const int32_t* tick,
+                  const float* x, const float* yaw_start, const float* com_start, float* x_des,
+                  float* r, uint8_t* mask, void* stream);
+
+/* Closed-loop plant for BASELINE config 5 (DART is unavailable: single-rigid-body forward
+ * Euler with the applied first-stage forces U[:,0,:] and the true lever arms r[:,0]), plus
+ * the reference-accumulator advance of src/mpc.py:261-262 and `*tick += 1`.
+ * track_err [B,2] accumulates |p-p_des|^2 and |Theta-Theta_des|^2. */
+int cmpc_plant_step(cmpc_handle* h, int32_t B, const cmpc_gait_tables* gt, int32_t* tick,
+                    float* x, const float* r, const float* U, const float* x_des,
+                    float* yaw_start, float* com_start, float* track_err, void* stream);
+
 /* Number of kernels this library has launched on behalf of `h` since creation. */
 int64_t cmpc_launch_count(const cmpc_handle* h);
 

@@ -23,7 +23,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 #: every symbol include/cmpc.h declares
 SYMBOLS = ("cmpc_default_config", "cmpc_create", "cmpc_destroy", "cmpc_solve", "cmpc_solve_host",
            "cmpc_condense", "cmpc_reset_warm", "cmpc_get_warm", "cmpc_set_warm",
-           "cmpc_launch_count", "cmpc_supported_horizons", "cmpc_version", "cmpc_last_error")
+           "cmpc_launch_count", "cmpc_supported_horizons", "cmpc_version", "cmpc_last_error",
+           "cmpc_assemble", "cmpc_plant_step")
 
 
 class CmpcError(RuntimeError):
@@ -44,6 +45,14 @@ class Config(C.Structure):
                 ("rho_min", C.c_float), ("rho_max", C.c_float),
                 ("kernel_variant", C.c_int32), ("lpt_schedule", C.c_int32),
                 ("device", C.c_int32)]
+
+
+class GaitTables(C.Structure):
+    """Mirror of ``struct cmpc_gait_tables`` (device pointers)."""
+    _fields_ = [("plan_pos", C.c_void_p), ("feet_id", C.c_void_p), ("ss", C.c_void_p),
+                ("ds", C.c_void_p), ("v_ref", C.c_void_p), ("omega_ref", C.c_void_p),
+                ("rp0", C.c_void_p), ("S", C.c_int32), ("total_steps", C.c_int32),
+                ("step_height", C.c_float), ("g", C.c_float)]
 
 
 def needs_build() -> bool:
@@ -91,6 +100,9 @@ def lib() -> C.CDLL:
     L.cmpc_reset_warm.argtypes = [vp, u8p]
     L.cmpc_get_warm.argtypes = [vp, i32, i32, f32p, f32p, vp]
     L.cmpc_set_warm.argtypes = [vp, i32, i32, f32p, f32p, vp]
+    gtp = C.POINTER(GaitTables)
+    L.cmpc_assemble.argtypes = [vp, i32, gtp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.cmpc_plant_step.argtypes = [vp, i32, gtp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.cmpc_launch_count.argtypes = [vp]
     L.cmpc_launch_count.restype = C.c_int64
     L.cmpc_supported_horizons.argtypes = [C.POINTER(C.c_int32), i32]

@@ -83,10 +83,17 @@ namespace {
 using SolveLaunch = cudaError_t (*)(const cmpc::SolveParams&, cudaStream_t);
 using CondenseLaunch = cudaError_t (*)(const cmpc::CondenseParams&, cudaStream_t);
 using ScoreLaunch = cudaError_t (*)(const cmpc::ScoreParams&, cudaStream_t);
+using AssembleLaunch = cudaError_t (*)(const cmpc::AssembleParams&, cudaStream_t);
 
 template <int N, int SPLIT, int MINB>
 cudaError_t launch_solve(const cmpc::SolveParams& p, cudaStream_t s) {
   cmpc::solve_kernel<N, SPLIT, MINB><<<p.B, cmpc::Geo<N, SPLIT>::THREADS, 0, s>>>(p);
+  return cudaGetLastError();
+}
+template <int N>
+cudaError_t launch_assemble(const cmpc::AssembleParams& p, cudaStream_t s) {
+  const int total = p.B * (N + 1);
+  cmpc::assemble_kernel<N><<<(total + 127) / 128, 128, 0, s>>>(p);
   return cudaGetLastError();
 }
 template <int N>
@@ -105,19 +112,20 @@ struct HorizonEntry {
   SolveLaunch solve[3];      // thread-layout variants (nullptr = not compiled)
   CondenseLaunch condense;
   ScoreLaunch score;
+  AssembleLaunch assemble;
 };
 
 // Horizons with compiled kernels.  <N, SPLIT, MINB>: SPLIT threads share one row of the
 // 6N x 6N wrench matrix so that the register-resident row slice stays <= 60 floats.
 const HorizonEntry kHorizons[] = {
-    {4, {launch_solve<4, 1, 8>, nullptr, nullptr}, launch_condense<4>, launch_score<4>},
-    {5, {launch_solve<5, 1, 8>, nullptr, nullptr}, launch_condense<5>, launch_score<5>},
-    {8, {launch_solve<8, 1, 8>, nullptr, nullptr}, launch_condense<8>, launch_score<8>},
-    {10, {launch_solve<10, 1, 8>, launch_solve<10, 2, 4>, launch_solve<10, 4, 2>}, launch_condense<10>, launch_score<10>},
-    {12, {launch_solve<12, 2, 4>, nullptr, nullptr}, launch_condense<12>, launch_score<12>},
-    {16, {launch_solve<16, 2, 3>, nullptr, nullptr}, launch_condense<16>, launch_score<16>},
-    {20, {launch_solve<20, 2, 2>, nullptr, nullptr}, launch_condense<20>, launch_score<20>},
-    {30, {launch_solve<30, 4, 1>, nullptr, nullptr}, launch_condense<30>, launch_score<30>},
+    {4, {launch_solve<4, 1, 8>, nullptr, nullptr}, launch_condense<4>, launch_score<4>, launch_assemble<4>},
+    {5, {launch_solve<5, 1, 8>, nullptr, nullptr}, launch_condense<5>, launch_score<5>, launch_assemble<5>},
+    {8, {launch_solve<8, 1, 8>, nullptr, nullptr}, launch_condense<8>, launch_score<8>, launch_assemble<8>},
+    {10, {launch_solve<10, 1, 8>, launch_solve<10, 2, 4>, launch_solve<10, 4, 2>}, launch_condense<10>, launch_score<10>, launch_assemble<10>},
+    {12, {launch_solve<12, 2, 4>, nullptr, nullptr}, launch_condense<12>, launch_score<12>, launch_assemble<12>},
+    {16, {launch_solve<16, 2, 3>, nullptr, nullptr}, launch_condense<16>, launch_score<16>, launch_assemble<16>},
+    {20, {launch_solve<20, 2, 2>, nullptr, nullptr}, launch_condense<20>, launch_score<20>, launch_assemble<20>},
+    {30, {launch_solve<30, 4, 1>, nullptr, nullptr}, launch_condense<30>, launch_score<30>, launch_assemble<30>},
 };
 
 const HorizonEntry* find_horizon(int N) {
@@ -392,6 +400,68 @@ int cmpc_condense(cmpc_handle* h, int32_t B, const float* x0, const float* r, co
   p.r_weight = c.r_weight;
   CUDA_TRY(find_horizon(c.N)->condense(p, (cudaStream_t)stream));
   h->launches.fetch_add(1);
+  return CMPC_OK;
+}
+
+namespace {
+void fill_gait(const cmpc_handle* h, const cmpc_gait_tables* g, cmpc::GaitTables& o) {
+  o.plan_pos = g->plan_pos; o.feet_id = g->feet_id; o.ss = g->ss; o.ds = g->ds;
+  o.v_ref = g->v_ref; o.omega_ref = g->omega_ref; o.rp0 = g->rp0;
+  o.S = g->S; o.total_steps = g->total_steps; o.step_height = g->step_height; o.g = g->g;
+  o.dt = h->cfg.dt;
+}
+int check_gait(const cmpc_gait_tables* g) {
+  if (!g || !g->plan_pos || !g->feet_id || !g->ss || !g->ds || !g->v_ref || !g->omega_ref || !g->rp0)
+    return fail(CMPC_ERR_INVALID, "null gait table pointer");
+  if (g->S <= 0) return fail(CMPC_ERR_INVALID, "gait tables need at least one step");
+  return CMPC_OK;
+}
+}  // namespace
+
+int cmpc_assemble(cmpc_handle* h, int32_t B, const cmpc_gait_tables* gt, const int32_t* tick,
+                  const float* x, const float* yaw_start, const float* com_start, float* x_des,
+                  float* r, uint8_t* mask, void* stream) {
+  if (!h) return fail(CMPC_ERR_INVALID, "null handle");
+  if (B < 0) return fail(CMPC_ERR_INVALID, "negative batch");
+  int rc = check_gait(gt);
+  if (rc) return rc;
+  if (B == 0) return CMPC_OK;
+  if (!tick || !x || !yaw_start || !com_start || !x_des || !r || !mask)
+    return fail(CMPC_ERR_INVALID, "null pointer");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  cmpc::AssembleParams p{};
+  fill_gait(h, gt, p.gt);
+  p.tick = tick; p.x = x; p.yaw_start = yaw_start; p.com_start = com_start;
+  p.x_des = x_des; p.r = r; p.mask = mask; p.B = B;
+  CUDA_TRY(find_horizon(h->cfg.N)->assemble(p, (cudaStream_t)stream));
+  h->launches.fetch_add(1);
+  return CMPC_OK;
+}
+
+int cmpc_plant_step(cmpc_handle* h, int32_t B, const cmpc_gait_tables* gt, int32_t* tick, float* x,
+                    const float* r, const float* U, const float* x_des, float* yaw_start,
+                    float* com_start, float* track_err, void* stream) {
+  if (!h) return fail(CMPC_ERR_INVALID, "null handle");
+  if (B < 0) return fail(CMPC_ERR_INVALID, "negative batch");
+  int rc = check_gait(gt);
+  if (rc) return rc;
+  if (!tick || ((!x || !r || !U || !x_des || !yaw_start || !com_start || !track_err) && B > 0))
+    return fail(CMPC_ERR_INVALID, "null pointer");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (B > 0) {
+    cmpc::PlantParams p{};
+    fill_gait(h, gt, p.gt);
+    p.tick = tick; p.x = x; p.r = r; p.U = U; p.x_des = x_des; p.yaw_start = yaw_start;
+    p.com_start = com_start; p.track_err = track_err; p.B = B; p.N = h->cfg.N;
+    p.inv_mass = 1.0f / h->cfg.mass;
+    for (int i = 0; i < 3; ++i) p.ib[i] = h->cfg.ibody_inv[i];
+    cmpc::plant_kernel<<<(B + 127) / 128, 128, 0, s>>>(p);
+    CUDA_TRY(cudaGetLastError());
+  }
+  cmpc::tick_kernel<<<1, 1, 0, s>>>(tick);
+  CUDA_TRY(cudaGetLastError());
+  h->launches.fetch_add(B > 0 ? 2 : 1);
   return CMPC_OK;
 }
 

@@ -784,4 +784,169 @@ __global__ void __launch_bounds__(256) condense_kernel(const CondenseParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// On-device parameter assembly and SRBD plant step.
+// Replaces the Python loops of reference src/mpc.py:178-255 (x_des, lever arms, contact
+// schedule) with one thread per (robot, stage); contact masks are integer arithmetic and
+// bit-exact with src/footstep_planner.py:226-246.
+// ---------------------------------------------------------------------------------------
+struct GaitTables {
+  const float* __restrict__ plan_pos;    // [B,S,4,3]
+  const uint8_t* __restrict__ feet_id;   // [B,S] stance bits of the single-support part
+  const int32_t* __restrict__ ss;        // [B]
+  const int32_t* __restrict__ ds;        // [B]
+  const float* __restrict__ v_ref;       // [B,3]
+  const float* __restrict__ omega_ref;   // [B]
+  const float* __restrict__ rp0;         // [B,2] initial roll, pitch
+  int32_t S, total_steps;
+  float step_height, g, dt;
+};
+
+// foot position the MPC look-ahead uses at tick `tk` (reference MPC.update_r_num,
+// src/mpc.py:306-318 + src/foot_trajectory_generator.py:27-96) and the stance bits of that tick
+__device__ __forceinline__ int lookahead(const GaitTables& gt, int b, int tk, float foot[4][3]) {
+  const int ss = gt.ss[b], period = ss + gt.ds[b];
+  int step = tk / period;
+  if (step > gt.S - 1) step = gt.S - 1;
+  const int tin = tk - step * period;
+  const int bits = (tin < ss) ? (int)gt.feet_id[(size_t)b * gt.S + step] : 0xF;
+  const int nxt = step + 1 < gt.S ? step + 1 : gt.S - 1;
+  const float* p0 = gt.plan_pos + ((size_t)b * gt.S + step) * 12;
+  const float* p1 = gt.plan_pos + ((size_t)b * gt.S + nxt) * 12;
+  const float ts = 0.8f * (float)ss, t = (float)tin;
+  const float u = t / ts;
+  const float blend = u * u * (3.f - 2.f * u);                // -2 u^3 + 3 u^2
+  const float bump = 16.f * gt.step_height * u * u * (u - 1.f) * (u - 1.f);   // 16h (u^4 - 2u^3 + u^2)
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const bool stance = (bits >> l) & 1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float a = p0[3 * l + k], c = p1[3 * l + k];
+      float v = a;
+      if (!stance && step != 0) {
+        if (t >= ts) v = c;
+        else v = (k == 2) ? a + bump : a + (c - a) * blend;
+      }
+      foot[l][k] = v;
+    }
+  }
+  return bits;
+}
+
+struct AssembleParams {
+  GaitTables gt;
+  const int32_t* __restrict__ tick;      // [1] current tick (device)
+  const float* __restrict__ x;           // [B,13] measured state
+  const float* __restrict__ yaw_start;   // [B]
+  const float* __restrict__ com_start;   // [B,3]
+  float* __restrict__ x_des;             // [B,N+1,13]
+  float* __restrict__ r;                 // [B,N,4,3]
+  uint8_t* __restrict__ mask;            // [B,N]
+  int32_t B;
+};
+
+template <int N>
+__global__ void __launch_bounds__(128) assemble_kernel(const AssembleParams p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.B * (N + 1)) return;
+  const int b = idx / (N + 1), i = idx % (N + 1);
+  const GaitTables& gt = p.gt;
+  const int t = *p.tick;
+  const int period = gt.ss[b] + gt.ds[b];
+  int step_now = t / period;
+  if (step_now > gt.S - 1) step_now = gt.S - 1;
+  const bool last = step_now == gt.total_steps - 1;          // src/mpc.py:181-183
+  const float vx = last ? 0.f : gt.v_ref[3 * b], vy = last ? 0.f : gt.v_ref[3 * b + 1],
+              vz = last ? 0.f : gt.v_ref[3 * b + 2], om = last ? 0.f : gt.omega_ref[b];
+  const float fi = (float)i;
+  float* xd = p.x_des + ((size_t)b * (N + 1) + i) * 13;       // src/mpc.py:202-214
+  const float cx = p.com_start[3 * b] + fi * vx * gt.dt, cy = p.com_start[3 * b + 1] + fi * vy * gt.dt,
+              cz = p.com_start[3 * b + 2] + fi * vz * gt.dt;
+  xd[0] = gt.rp0[2 * b]; xd[1] = gt.rp0[2 * b + 1]; xd[2] = p.yaw_start[b] + fi * om * gt.dt;
+  xd[3] = cx; xd[4] = cy; xd[5] = cz;
+  xd[6] = 0.f; xd[7] = 0.f; xd[8] = om;
+  xd[9] = vx; xd[10] = vy; xd[11] = vz; xd[12] = gt.g;
+  if (i == N) return;
+  float foot[4][3];
+  const int bits = lookahead(gt, b, t + i, foot);
+  p.mask[(size_t)b * N + i] = (uint8_t)bits;                  // src/mpc.py:249-254
+  const float* xs = p.x + (size_t)b * 13;
+  const float ox = i == 0 ? xs[3] : cx, oy = i == 0 ? xs[4] : cy, oz = i == 0 ? xs[5] : cz;
+  float* rr = p.r + ((size_t)b * N + i) * 12;                 // src/mpc.py:218-239
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    rr[3 * l] = foot[l][0] - ox; rr[3 * l + 1] = foot[l][1] - oy; rr[3 * l + 2] = foot[l][2] - oz;
+  }
+}
+
+// SRBD forward-Euler plant with the applied first-stage forces and the true lever arms
+// (the same model the MPC predicts with, reference src/mpc.py:86-117), plus the reference
+// accumulator update of src/mpc.py:261-262 and a running tracking-error sum.
+struct PlantParams {
+  GaitTables gt;
+  int32_t* __restrict__ tick;            // [1], advanced by thread 0 of block 0 of the NEXT kernel
+  float* __restrict__ x;                 // [B,13]
+  const float* __restrict__ r;           // [B,N,4,3] (stage 0 is used)
+  const float* __restrict__ U;           // [B,N,12]
+  const float* __restrict__ x_des;       // [B,N+1,13]
+  float* __restrict__ yaw_start;
+  float* __restrict__ com_start;
+  float* __restrict__ track_err;         // [B,2] accumulated |p - p_des|^2, |Theta - Theta_des|^2
+  int32_t B, N;
+  float inv_mass;
+  float ib[3];
+};
+
+__global__ void __launch_bounds__(128) plant_kernel(const PlantParams p) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.B) return;
+  const GaitTables& gt = p.gt;
+  const int t = *p.tick;
+  float* x = p.x + (size_t)b * 13;
+  const float* u = p.U + (size_t)b * p.N * 12;
+  const float* r0 = p.r + (size_t)b * p.N * 12;
+  const float* xd = p.x_des + (size_t)b * (p.N + 1) * 13;
+  float sn, cs;
+  sincosf(x[2], &sn, &cs);
+  // net force and torque
+  float fx = 0.f, fy = 0.f, fz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const float ax = u[3 * l], ay = u[3 * l + 1], az = u[3 * l + 2];
+    const float rx = r0[3 * l], ry = r0[3 * l + 1], rz = r0[3 * l + 2];
+    fx += ax; fy += ay; fz += az;
+    tx += ry * az - rz * ay; ty += rz * ax - rx * az; tz += rx * ay - ry * ax;
+  }
+  // omega_dot = Rz diag(ib) Rz' tau
+  const float bx = p.ib[0] * (cs * tx + sn * ty), by = p.ib[1] * (-sn * tx + cs * ty), bz = p.ib[2] * tz;
+  const float wdx = cs * bx - sn * by, wdy = sn * bx + cs * by, wdz = bz;
+  const float dt = gt.dt;
+  const float wx = x[6], wy = x[7], wz = x[8];
+  // tracking error of the state the controller saw
+  const float ep = (x[3] - xd[3]) * (x[3] - xd[3]) + (x[4] - xd[4]) * (x[4] - xd[4]) + (x[5] - xd[5]) * (x[5] - xd[5]);
+  const float et = (x[0] - xd[0]) * (x[0] - xd[0]) + (x[1] - xd[1]) * (x[1] - xd[1]) + (x[2] - xd[2]) * (x[2] - xd[2]);
+  p.track_err[2 * b] += ep;
+  p.track_err[2 * b + 1] += et;
+  // X+ = X + dt (A X + B u):  Theta' = Rz w, p' = v, w' = I^-1 tau, v' = f/m + g e_z
+  x[0] += dt * (cs * wx - sn * wy);
+  x[1] += dt * (sn * wx + cs * wy);
+  x[2] += dt * wz;
+  x[3] += dt * x[9]; x[4] += dt * x[10]; x[5] += dt * x[11];
+  x[6] += dt * wdx; x[7] += dt * wdy; x[8] += dt * wdz;
+  x[9] += dt * fx * p.inv_mass; x[10] += dt * fy * p.inv_mass; x[11] += dt * (fz * p.inv_mass + x[12]);
+  // reference accumulators (src/mpc.py:261-262), zeroed references during the last planned step
+  const int period = gt.ss[b] + gt.ds[b];
+  int step_now = t / period;
+  if (step_now > gt.S - 1) step_now = gt.S - 1;
+  if (step_now != gt.total_steps - 1) {
+    p.com_start[3 * b] += gt.v_ref[3 * b] * dt;
+    p.com_start[3 * b + 1] += gt.v_ref[3 * b + 1] * dt;
+    p.com_start[3 * b + 2] += gt.v_ref[3 * b + 2] * dt;
+    p.yaw_start[b] += gt.omega_ref[b] * dt;
+  }
+}
+
+__global__ void tick_kernel(int32_t* tick) { *tick += 1; }
+
 }  // namespace cmpc

@@ -1,0 +1,20 @@
+"""BASELINE config 5: closed-loop warm-started MPC rollouts, 8192 robots, friction sweep 0.3-1.0."""
+import sys, os, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import mpc_b200 as pkg
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+for warm_mode, graph in ((1, True), (2, True), (1, False)):
+    ro = pkg.ClosedLoopRollout(B, N=10, gaits=("trot",), mu=(0.3, 1.0), seed=0, warm_mode=warm_mode)
+    ro.run(21, use_graph=graph, ticks_per_graph=20)       # warm-up + capture
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter(); e0.record()
+    done = ro.run(T, use_graph=graph, ticks_per_graph=20)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    s = ro.summary()
+    print(json.dumps(dict(config="closed loop, %d robots x %d ticks, trot, mu 0.3-1.0" % (B, done), warm_mode=warm_mode,
+                          cuda_graph=graph, ms_per_tick=ms / done, robot_ticks_per_s=B * done / (ms * 1e-3),
+                          wall_s=time.perf_counter() - t0, **s)), flush=True)

@@ -204,8 +204,9 @@ def run_ours(args):
 
     # --- end to end: host (pinned) buffers through cmpc_solve_host, copies inside the timing ----
     hin = [t.numpy() for t in pinned]
-    hout = (np.empty((B, N, 12), np.float32), None, np.empty((B,), np.int32),
-            np.empty((B,), np.float32), np.empty((B,), np.float32), np.empty((B,), np.int32))
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    hout = (pin((B, N, 12), torch.float32), None, pin((B,), torch.int32),
+            pin((B,), torch.float32), pin((B,), torch.float32), pin((B,), torch.int32))
     for _ in range(3):
         mpc.solve_host(*hin, want_X=False, out=hout)
     barrier()

@@ -58,7 +58,7 @@ struct Staging {
   char* d_in = nullptr;
   char* d_out = nullptr;
   size_t in_bytes = 0, out_bytes = 0;
-  cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t streams[2] = {nullptr, nullptr};
   int cap = 0;             // problems
 };
 
@@ -171,19 +171,19 @@ void fill_solve_params(const cmpc_handle* h, cmpc::SolveParams& p) {
 
 // Enqueue the LPT ordering of a batch (2 small kernels) and point p.order at it.
 // `order_off` lets the host path order several chunks independently.
-int schedule_batch(cmpc_handle* h, cmpc::SolveParams& p, int order_off, cudaStream_t s) {
+int schedule_batch(cmpc_handle* h, cmpc::SolveParams& p, int order_off, int hist_slot, cudaStream_t s) {
   p.order = nullptr;
   if (!h->cfg.lpt_schedule || p.B < h->cfg.lpt_schedule) return CMPC_OK;
   const cmpc_config& c = h->cfg;
   cmpc::ScoreParams sp{};
   sp.x0 = p.x0; sp.r = p.r; sp.mask = p.mask; sp.Mg = h->d_Mg;
   sp.score = h->d_score + order_off;
-  sp.hist = h->d_hist;
+  sp.hist = h->d_hist + 64 * hist_slot;
   sp.B = p.B;
   sp.inv_mass = 1.0f / c.mass;
   for (int i = 0; i < 3; ++i) sp.ib[i] = c.ibody_inv[i];
   CUDA_TRY(find_horizon(c.N)->score(sp, s));
-  cmpc::order_kernel<<<1, 1024, 0, s>>>(sp.score, h->d_hist, h->d_order + order_off, p.B);
+  cmpc::order_kernel<<<1, 1024, 0, s>>>(sp.score, sp.hist, h->d_order + order_off, p.B);
   CUDA_TRY(cudaGetLastError());
   h->launches.fetch_add(2);
   p.order = h->d_order + order_off;
@@ -324,13 +324,13 @@ int cmpc_create(const cmpc_config* cfg, cmpc_handle** out) {
       (e = cudaMalloc(&h->d_warm_valid, slots)) != cudaSuccess ||
       (e = cudaMalloc(&h->d_score, slots * sizeof(float))) != cudaSuccess ||
       (e = cudaMalloc(&h->d_order, slots * sizeof(int32_t))) != cudaSuccess ||
-      (e = cudaMalloc(&h->d_hist, 64 * sizeof(int32_t))) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_hist, 4 * 64 * sizeof(int32_t))) != cudaSuccess ||
       (e = cudaMemcpy(h->d_Minv, Mif.data(), mbytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemcpy(h->d_Mg, Mf.data(), mbytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemset(h->d_warm_x, 0, slots * 12 * N * sizeof(float))) != cudaSuccess ||
       (e = cudaMemset(h->d_warm_y, 0, slots * 12 * N * sizeof(float))) != cudaSuccess ||
       (e = cudaMemset(h->d_warm_valid, 0, slots)) != cudaSuccess ||
-      (e = cudaMemset(h->d_hist, 0, 64 * sizeof(int32_t))) != cudaSuccess) {
+      (e = cudaMemset(h->d_hist, 0, 4 * 64 * sizeof(int32_t))) != cudaSuccess) {
     cmpc_destroy(h);
     return fail(CMPC_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
   }
@@ -375,7 +375,7 @@ int cmpc_solve(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, const 
   p.U = U; p.X = X; p.iters = iters; p.pri_res = pri_res; p.dua_res = dua_res; p.status = status;
   p.B = B;
   p.slot0 = slot0;
-  rc = schedule_batch(h, p, 0, (cudaStream_t)stream);
+  rc = schedule_batch(h, p, 0, 0, (cudaStream_t)stream);
   if (rc) return rc;
   CUDA_TRY(pick_solve(h->cfg)(p, (cudaStream_t)stream));
   h->launches.fetch_add(1);
@@ -493,6 +493,19 @@ Layout make_layout(int N, int C, bool withX) {
 }
 }  // namespace
 
+namespace {
+// true if `ptr` is page-locked host memory the DMA engines can read/write directly
+bool is_pinned(const void* ptr) {
+  if (!ptr) return true;
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+}  // namespace
+
 int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, const float* r,
                     const uint8_t* mask, const float* x_des, const float* mu, float* U, float* X,
                     int32_t* iters, float* pri_res, float* dua_res, int32_t* status) {
@@ -503,18 +516,24 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, c
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   const int N = h->cfg.N;
   Staging& st = h->st;
-  // chunking: overlap H2D(i+1) / solve(i) / D2H(i-1) on three streams
-  const int nchunk = B >= 2048 ? 4 : (B >= 512 ? 2 : 1);
+  // Two chunks on two streams: H2D(1) overlaps solve(0), D2H(0) overlaps solve(1).  More
+  // chunks would give every chunk its own straggler tail.
+  const int nchunk = B >= 2048 ? 2 : 1;
   const int C = (B + nchunk - 1) / nchunk;
+  // page-locked caller buffers are copied directly by the DMA engines; pageable ones are
+  // staged through the handle's pinned arenas
+  const bool in_pinned = is_pinned(x0) && is_pinned(r) && is_pinned(mask) && is_pinned(x_des) && is_pinned(mu);
+  const bool out_pinned = is_pinned(U) && is_pinned(X) && is_pinned(iters) && is_pinned(pri_res) &&
+                          is_pinned(dua_res) && is_pinned(status);
   const Layout L = make_layout(N, C, true);
-  if (st.cap < C || !st.h_in) {
+  if (st.cap < C || !st.d_in) {
     if (st.h_in) cudaFreeHost(st.h_in);
     if (st.h_out) cudaFreeHost(st.h_out);
     cudaFree(st.d_in);
     cudaFree(st.d_out);
     st.h_in = st.h_out = st.d_in = st.d_out = nullptr;
     st.cap = 0;
-    const size_t nb = 4;   // arenas per direction (>= nchunk)
+    const size_t nb = 2;   // arenas per direction (= max chunks)
     CUDA_TRY(cudaMallocHost(&st.h_in, L.in_total * nb));
     CUDA_TRY(cudaMallocHost(&st.h_out, L.out_total * nb));
     CUDA_TRY(cudaMalloc(&st.d_in, L.in_total * nb));
@@ -529,20 +548,29 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, c
   cmpc::SolveParams base{};
   fill_solve_params(h, base);
   const SolveLaunch solve_fn = pick_solve(h->cfg);
+  const size_t nx = (size_t)13 * (N + 1), nu = (size_t)12 * N;
   for (int ci = 0; ci < nchunk; ++ci) {
     const int lo = ci * C, n = (lo + C <= B ? C : B - lo);
     if (n <= 0) break;
-    cudaStream_t s = st.streams[ci % 3];
+    cudaStream_t s = st.streams[ci];
     char* hin = st.h_in + (size_t)ci * st.in_bytes;
     char* din = st.d_in + (size_t)ci * st.in_bytes;
     char* dout = st.d_out + (size_t)ci * st.out_bytes;
     char* hout = st.h_out + (size_t)ci * st.out_bytes;
-    std::memcpy(hin + La.x0, x0 + (size_t)lo * 13, (size_t)n * 13 * 4);
-    std::memcpy(hin + La.r, r + (size_t)lo * 12 * N, (size_t)n * 12 * N * 4);
-    std::memcpy(hin + La.xdes, x_des + (size_t)lo * 13 * (N + 1), (size_t)n * 13 * (N + 1) * 4);
-    std::memcpy(hin + La.mu, mu + lo, (size_t)n * 4);
-    std::memcpy(hin + La.mask, mask + (size_t)lo * N, (size_t)n * N);
-    CUDA_TRY(cudaMemcpyAsync(din, hin, La.in_total, cudaMemcpyHostToDevice, s));
+    if (in_pinned) {
+      CUDA_TRY(cudaMemcpyAsync(din + La.x0, x0 + (size_t)lo * 13, (size_t)n * 13 * 4, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaMemcpyAsync(din + La.r, r + (size_t)lo * nu, (size_t)n * nu * 4, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaMemcpyAsync(din + La.xdes, x_des + (size_t)lo * nx, (size_t)n * nx * 4, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaMemcpyAsync(din + La.mu, mu + lo, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaMemcpyAsync(din + La.mask, mask + (size_t)lo * N, (size_t)n * N, cudaMemcpyHostToDevice, s));
+    } else {
+      std::memcpy(hin + La.x0, x0 + (size_t)lo * 13, (size_t)n * 13 * 4);
+      std::memcpy(hin + La.r, r + (size_t)lo * nu, (size_t)n * nu * 4);
+      std::memcpy(hin + La.xdes, x_des + (size_t)lo * nx, (size_t)n * nx * 4);
+      std::memcpy(hin + La.mu, mu + lo, (size_t)n * 4);
+      std::memcpy(hin + La.mask, mask + (size_t)lo * N, (size_t)n * N);
+      CUDA_TRY(cudaMemcpyAsync(din, hin, La.in_total, cudaMemcpyHostToDevice, s));
+    }
     cmpc::SolveParams p = base;
     p.x0 = (const float*)(din + La.x0);
     p.r = (const float*)(din + La.r);
@@ -557,20 +585,30 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, c
     p.status = (int32_t*)(dout + La.status);
     p.B = n;
     p.slot0 = slot0 + lo;
-    // chunks run on different streams but share the 64-bin histogram: order on one stream
-    p.order = nullptr;
+    rc = schedule_batch(h, p, lo, ci, s);
+    if (rc) return rc;
     CUDA_TRY(solve_fn(p, s));
     h->launches.fetch_add(1);
-    const size_t out_n = X ? La.out_total : La.X;
-    CUDA_TRY(cudaMemcpyAsync(hout, dout, out_n, cudaMemcpyDeviceToHost, s));
+    if (out_pinned) {
+      CUDA_TRY(cudaMemcpyAsync(U + (size_t)lo * nu, dout + La.U, (size_t)n * nu * 4, cudaMemcpyDeviceToHost, s));
+      if (X) CUDA_TRY(cudaMemcpyAsync(X + (size_t)lo * nx, dout + La.X, (size_t)n * nx * 4, cudaMemcpyDeviceToHost, s));
+      if (iters) CUDA_TRY(cudaMemcpyAsync(iters + lo, dout + La.iters, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+      if (pri_res) CUDA_TRY(cudaMemcpyAsync(pri_res + lo, dout + La.pri, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+      if (dua_res) CUDA_TRY(cudaMemcpyAsync(dua_res + lo, dout + La.dua, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+      if (status) CUDA_TRY(cudaMemcpyAsync(status + lo, dout + La.status, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    } else {
+      const size_t out_n = X ? La.out_total : La.X;
+      CUDA_TRY(cudaMemcpyAsync(hout, dout, out_n, cudaMemcpyDeviceToHost, s));
+    }
   }
   for (int ci = 0; ci < nchunk; ++ci) {
     const int lo = ci * C, n = (lo + C <= B ? C : B - lo);
     if (n <= 0) break;
-    CUDA_TRY(cudaStreamSynchronize(st.streams[ci % 3]));
+    CUDA_TRY(cudaStreamSynchronize(st.streams[ci]));
+    if (out_pinned) continue;
     const char* hout = st.h_out + (size_t)ci * st.out_bytes;
-    std::memcpy(U + (size_t)lo * 12 * N, hout + La.U, (size_t)n * 12 * N * 4);
-    if (X) std::memcpy(X + (size_t)lo * 13 * (N + 1), hout + La.X, (size_t)n * 13 * (N + 1) * 4);
+    std::memcpy(U + (size_t)lo * nu, hout + La.U, (size_t)n * nu * 4);
+    if (X) std::memcpy(X + (size_t)lo * nx, hout + La.X, (size_t)n * nx * 4);
     if (iters) std::memcpy(iters + lo, hout + La.iters, (size_t)n * 4);
     if (pri_res) std::memcpy(pri_res + lo, hout + La.pri, (size_t)n * 4);
     if (dua_res) std::memcpy(dua_res + lo, hout + La.dua, (size_t)n * 4);

@@ -165,7 +165,8 @@ solve_kernel(const SolveParams p) {
   __shared__ __align__(16) float s_G[NLEG][12];        // Ghat (9) + dxy, dz, pad per leg
   __shared__ __align__(16) float s_row[2][NWP + 4];    // pivot-row double buffer (+ 1/pivot)
   __shared__ __align__(16) float s_s[NWP];             // wrench-space rhs  s = G D^-1 b
-  __shared__ __align__(16) float s_q[NWP];             // q = P^-1 s   (also: w, v scratch)
+  __shared__ __align__(16) float s_q[SPLIT][NWP];      // q = P^-1 s as SPLIT partial sums
+  __shared__ __align__(16) float s_v[NWP];             // exact gradient M G x (refresh)
   __shared__ __align__(16) float s_h[NWP];             // linear term h
   __shared__ __align__(16) float s_S[NWP];             // Jacobi scaling 1/sqrt(P_ii) of the sweep
   __shared__ float s_red[2][LWARPS][8];
@@ -182,7 +183,7 @@ solve_kernel(const SolveParams p) {
   for (int i = tid; i < 13; i += THREADS) s_x0[i] = __ldg(p.x0 + (size_t)b * 13 + i);
   for (int i = tid; i < NX; i += THREADS) s_xd[i] = __ldg(p.x_des + (size_t)b * NX + i);
   for (int i = tid; i < N; i += THREADS) s_mask[i] = (int)__ldg(p.mask + (size_t)b * N + i);
-  for (int i = tid; i < NWP; i += THREADS) { s_s[i] = 0.f; s_q[i] = 0.f; s_h[i] = 0.f; s_S[i] = 0.f; }
+  for (int i = tid; i < NWP; i += THREADS) { s_s[i] = 0.f; s_v[i] = 0.f; s_h[i] = 0.f; s_S[i] = 0.f; }
   const float mu = __ldg(p.mu + b);
   // issue every other global load of this problem now so that their DRAM latencies overlap
   const bool is_leg = tid < NLEG;
@@ -236,7 +237,8 @@ solve_kernel(const SolveParams p) {
     s_G[tid][11] = stance ? 1.f : 0.f;
   }
   const bool is_row = tid < G_::ROWT;
-  const int ri = tid / SPLIT, rs = tid % SPLIT;      // P row, slice
+  const int rs = SPLIT == 1 ? 0 : tid / NW;          // slice-major layout: slice, P row
+  const int ri = tid - rs * NW;                      // (any SPLIT works, no lane alignment needed)
   const int rj = ri / 6, ra = ri % 6;                // stage, axis of that row
   if (is_row && rs == 0) s_h[ri] = wrench_linear_term<N>(rj, ra, s_x0, s_xd, cs, sn, p.w, p.dt);
   __syncthreads();
@@ -284,7 +286,12 @@ solve_kernel(const SolveParams p) {
       float v = 0.f;
       if (col < NW) {
         if (a2 == ra) v = __ldg(mi + j2);
-        if (j2 == rj) v += E[a2];
+        if (j2 == rj) {       // select instead of E[a2]: no dynamically indexed local array
+          float e = 0.f;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) e = (a2 == q) ? E[q] : e;
+          v += e;
+        }
         v *= sc_i * s_S[col];
       }
       row[c] = v;
@@ -404,12 +411,12 @@ solve_kernel(const SolveParams p) {
       float acc = 0.f;
 #pragma unroll
       for (int j2 = 0; j2 < N; ++j2) acc = fmaf(__ldg(mg + j2), s_s[6 * j2 + ra], acc);
-      s_q[ri] = acc;
+      s_v[ri] = acc;
     }
     __syncthreads();
     if (is_leg && stance) {
 #pragma unroll
-      for (int a = 0; a < 6; ++a) vh[a] = s_q[6 * lj + a] + hj[a];
+      for (int a = 0; a < 6; ++a) vh[a] = s_v[6 * lj + a] + hj[a];
     }
     __syncthreads();
   };
@@ -523,32 +530,31 @@ solve_kernel(const SolveParams p) {
         }
       }
     }
-    // wrench phase: q = P^-1 s   (row holds -P^-1)
-    {
-      float acc = 0.f;
-      if (is_row) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        const float* sp = s_s + rs * COLS;
+    // wrench phase: q = P^-1 s   (row holds -P^-1); each slice publishes its partial sum
+    if (is_row) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const float* sp = s_s + rs * COLS;
 #pragma unroll
-        for (int c = 0; c < COLS; c += 4) {
-          const float4 sv4 = *reinterpret_cast<const float4*>(sp + c);
-          a0 = fmaf(row[c], sv4.x, a0);
-          a1 = fmaf(row[c + 1], sv4.y, a1);
-          a2 = fmaf(row[c + 2], sv4.z, a2);
-          a3 = fmaf(row[c + 3], sv4.w, a3);
-        }
-        acc = (a0 + a1) + (a2 + a3);
+      for (int c = 0; c < COLS; c += 4) {
+        const float4 sv4 = *reinterpret_cast<const float4*>(sp + c);
+        a0 = fmaf(row[c], sv4.x, a0);
+        a1 = fmaf(row[c + 1], sv4.y, a1);
+        a2 = fmaf(row[c + 2], sv4.z, a2);
+        a3 = fmaf(row[c + 3], sv4.w, a3);
       }
-      if (SPLIT >= 2) acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      if (SPLIT >= 4) acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      if (is_row && rs == 0) s_q[ri] = -acc;
+      s_q[rs][ri] = -((a0 + a1) + (a2 + a3));
     }
     __syncthreads();
     // leg phase B: x-update, relaxed projection, dual update
     if (is_leg && stance) {
       float qv[6];
 #pragma unroll
-      for (int a = 0; a < 6; ++a) qv[a] = s_q[6 * lj + a];
+      for (int a = 0; a < 6; ++a) {
+        float acc = s_q[0][6 * lj + a];
+#pragma unroll
+        for (int sl = 1; sl < SPLIT; ++sl) acc += s_q[sl][6 * lj + a];
+        qv[a] = acc;
+      }
 #pragma unroll
       for (int a = 0; a < 6; ++a) vh[a] = fmaf(alpha, qv[a], vh[a]);
       float w3[3];

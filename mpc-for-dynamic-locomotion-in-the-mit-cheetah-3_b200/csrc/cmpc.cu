@@ -3,6 +3,7 @@
 // CMPC_ERR_CUDA when the CUDA device or the kernels are unavailable.
 #include "../../include/cmpc.h"
 #include "cmpc_kernels.cuh"
+#include "cmpc_cluster.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -90,6 +91,23 @@ cudaError_t launch_solve(const cmpc::SolveParams& p, cudaStream_t s) {
   cmpc::solve_kernel<N, SPLIT, MINB><<<p.B, cmpc::Geo<N, SPLIT>::THREADS, 0, s>>>(p);
   return cudaGetLastError();
 }
+// one thread-block cluster of CL CTAs per problem (long horizons, see cmpc_cluster.cuh)
+template <int NL, int CL, int SPLIT, int MINB>
+cudaError_t launch_solve_cluster(const cmpc::SolveParams& p, cudaStream_t s) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(p.B * CL), 1, 1);
+  cfg.blockDim = dim3(cmpc::CGeo<NL, CL, SPLIT>::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, cmpc::solve_cluster_kernel<NL, CL, SPLIT, MINB>, p);
+}
 template <int N>
 cudaError_t launch_assemble(const cmpc::AssembleParams& p, cudaStream_t s) {
   const int total = p.B * (N + 1);
@@ -124,8 +142,10 @@ const HorizonEntry kHorizons[] = {
     {10, {launch_solve<10, 1, 8>, launch_solve<10, 2, 4>, launch_solve<10, 4, 2>}, launch_condense<10>, launch_score<10>, launch_assemble<10>},
     {12, {launch_solve<12, 2, 4>, nullptr, nullptr}, launch_condense<12>, launch_score<12>, launch_assemble<12>},
     {16, {launch_solve<16, 2, 3>, nullptr, nullptr}, launch_condense<16>, launch_score<16>, launch_assemble<16>},
-    {20, {launch_solve<20, 2, 2>, launch_solve<20, 3, 1>, nullptr}, launch_condense<20>, launch_score<20>, launch_assemble<20>},
-    {30, {launch_solve<30, 3, 1>, launch_solve<30, 4, 1>, nullptr}, launch_condense<30>, launch_score<30>, launch_assemble<30>},
+    {20, {launch_solve<20, 2, 2>, launch_solve<20, 3, 1>, launch_solve_cluster<10, 2, 2, 1>}, launch_condense<20>, launch_score<20>, launch_assemble<20>},
+    {30, {launch_solve<30, 3, 1>, launch_solve<30, 4, 1>, launch_solve_cluster<10, 3, 3, 1>}, launch_condense<30>, launch_score<30>, launch_assemble<30>},
+    {40, {launch_solve_cluster<10, 4, 4, 1>, nullptr, nullptr}, nullptr, launch_score<40>, launch_assemble<40>},
+    {60, {launch_solve_cluster<10, 6, 6, 1>, nullptr, nullptr}, nullptr, launch_score<60>, launch_assemble<60>},
 };
 
 const HorizonEntry* find_horizon(int N) {
@@ -398,6 +418,8 @@ int cmpc_condense(cmpc_handle* h, int32_t B, const float* x0, const float* r, co
   for (int i = 0; i < 3; ++i) p.ib[i] = c.ibody_inv[i];
   for (int i = 0; i < 13; ++i) p.w[i] = c.w[i];
   p.r_weight = c.r_weight;
+  if (!find_horizon(c.N)->condense)
+    return fail(CMPC_ERR_UNSUPPORTED, "cmpc_condense is not compiled for N=%d (dense H export needs N <= 30)", c.N);
   CUDA_TRY(find_horizon(c.N)->condense(p, (cudaStream_t)stream));
   h->launches.fetch_add(1);
   return CMPC_OK;

@@ -142,8 +142,8 @@ const HorizonEntry kHorizons[] = {
     {10, {launch_solve<10, 1, 8>, launch_solve<10, 2, 4>, launch_solve<10, 4, 2>}, launch_condense<10>, launch_score<10>, launch_assemble<10>},
     {12, {launch_solve<12, 2, 4>, nullptr, nullptr}, launch_condense<12>, launch_score<12>, launch_assemble<12>},
     {16, {launch_solve<16, 2, 3>, nullptr, nullptr}, launch_condense<16>, launch_score<16>, launch_assemble<16>},
-    {20, {launch_solve<20, 2, 2>, launch_solve<20, 3, 1>, launch_solve_cluster<10, 2, 2, 1>}, launch_condense<20>, launch_score<20>, launch_assemble<20>},
-    {30, {launch_solve<30, 3, 1>, launch_solve<30, 4, 1>, launch_solve_cluster<10, 3, 3, 1>}, launch_condense<30>, launch_score<30>, launch_assemble<30>},
+    {20, {launch_solve<20, 2, 2>, launch_solve<20, 3, 1>, launch_solve_cluster<10, 2, 2, 3>}, launch_condense<20>, launch_score<20>, launch_assemble<20>},
+    {30, {launch_solve<30, 3, 1>, launch_solve<30, 4, 1>, launch_solve_cluster<10, 3, 3, 2>}, launch_condense<30>, launch_score<30>, launch_assemble<30>},
     {40, {launch_solve_cluster<10, 4, 4, 1>, nullptr, nullptr}, nullptr, launch_score<40>, launch_assemble<40>},
     {60, {launch_solve_cluster<10, 6, 6, 1>, nullptr, nullptr}, nullptr, launch_score<60>, launch_assemble<60>},
 };

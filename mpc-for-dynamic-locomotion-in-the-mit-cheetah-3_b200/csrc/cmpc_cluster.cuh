@@ -47,7 +47,8 @@ solve_cluster_kernel(const SolveParams p) {
   __shared__ __align__(16) float s_x0[16];
   __shared__ __align__(16) float s_xd[NX + 3];
   __shared__ __align__(16) float s_G[NLEG][12];
-  __shared__ __align__(16) float s_row[2][NWP + 4];     // pivot rows, pushed by the owner CTA
+  constexpr int NB = NL;                                // pivots per cluster barrier (divides 6 NL)
+  __shared__ __align__(16) float s_row[2][NB][NWP + 4]; // pivot rows of one block, pushed by the owner CTA
   __shared__ __align__(16) float s_s[2][NWP];           // all-gathered wrench vectors
   __shared__ __align__(16) float s_q[SPLIT][NWL];       // q = P^-1 s (local rows), partial sums
   __shared__ __align__(16) float s_v[NWL];
@@ -76,7 +77,7 @@ solve_cluster_kernel(const SolveParams p) {
   float* r_red[CL];
 #pragma unroll
   for (int c = 0; c < CL; ++c) {
-    r_row[c] = cluster.map_shared_rank(&s_row[0][0], c);
+    r_row[c] = cluster.map_shared_rank(&s_row[0][0][0], c);
     r_s[c] = cluster.map_shared_rank(&s_s[0][0], c);
     r_S[c] = cluster.map_shared_rank(&s_S[0], c);
     r_red[c] = cluster.map_shared_rank(&s_red[0][0][0][0], c);
@@ -211,39 +212,64 @@ solve_cluster_kernel(const SolveParams p) {
       diag = (__ldg(mi + rj) + E[ra]) * sc_i * sc_i;
       rdiag = __fdividef(1.f, diag);
     }
-    for (int k = 0; k < NWT; ++k) {
-      const int boff = (k & 1) * (NWP + 4);
-      if (is_row && gi == k) {
+    // Blocked over NB pivots: the CTA that owns a block runs its NB steps with local barriers
+    // only (pushing each pivot row to every peer as it goes), one cluster barrier publishes the
+    // block, then the peers apply the NB pivots back to back from their local copies (each
+    // thread only touches its own row slice, so they need no barrier in between).  Buffers
+    // alternate with the block parity: nobody can be more than one block ahead.
+    auto apply_pivot = [&](const float* buf, int k) {
+      const float d = buf[NWP];
+      const float m = buf[gi];
+      const bool own = gi == k;
+      const float nf = own ? d - 1.f : -m * d;
+      diag = own ? -d : fmaf(nf, m, diag);
+      rdiag = __fdividef(1.f, diag);
+      const float* pr = buf + rs * COLS;
 #pragma unroll
-        for (int cc = 0; cc < CL; ++cc) {
-          float* buf = r_row[cc] + boff;
-#pragma unroll
-          for (int c = 0; c < COLS; c += 4)
-            *reinterpret_cast<float4*>(buf + rs * COLS + c) =
-                make_float4(row[c], row[c + 1], row[c + 2], row[c + 3]);
-          if (k / COLS == rs) {
-            buf[k] = diag - 1.f;
-            buf[NWP] = rdiag;
-          }
-        }
+      for (int c = 0; c < COLS; c += 4) {
+        const float4 pv = *reinterpret_cast<const float4*>(pr + c);
+        row[c] = fmaf(nf, pv.x, row[c]);
+        row[c + 1] = fmaf(nf, pv.y, row[c + 1]);
+        row[c + 2] = fmaf(nf, pv.z, row[c + 2]);
+        row[c + 3] = fmaf(nf, pv.w, row[c + 3]);
       }
-      cluster.sync();
-      if (is_row) {
-        const float* buf = &s_row[0][0] + boff;
-        const float d = buf[NWP];
-        const float m = buf[gi];
-        const bool own = gi == k;
-        const float nf = own ? d - 1.f : -m * d;
-        diag = own ? -d : fmaf(nf, m, diag);
-        rdiag = __fdividef(1.f, diag);
-        const float* pr = buf + rs * COLS;
+    };
+    for (int blk = 0; blk < NWT / NB; ++blk) {
+      const int k0 = blk * NB;
+      const int boff = (blk & 1) * NB * (NWP + 4);
+      if (rank == k0 / NWL) {
+        for (int j = 0; j < NB; ++j) {
+          const int k = k0 + j;
+          float* lbuf = &s_row[0][0][0] + boff + j * (NWP + 4);
+          if (is_row && gi == k) {
 #pragma unroll
-        for (int c = 0; c < COLS; c += 4) {
-          const float4 pv = *reinterpret_cast<const float4*>(pr + c);
-          row[c] = fmaf(nf, pv.x, row[c]);
-          row[c + 1] = fmaf(nf, pv.y, row[c + 1]);
-          row[c + 2] = fmaf(nf, pv.z, row[c + 2]);
-          row[c + 3] = fmaf(nf, pv.w, row[c + 3]);
+            for (int c = 0; c < COLS; c += 4)
+              *reinterpret_cast<float4*>(lbuf + rs * COLS + c) =
+                  make_float4(row[c], row[c + 1], row[c + 2], row[c + 3]);
+            if (k / COLS == rs) {
+              lbuf[k] = diag - 1.f;
+              lbuf[NWP] = rdiag;
+            }
+          }
+          __syncthreads();
+          {   // the whole CTA pushes the finished pivot row to the peers (fire and forget; the
+              // block's cluster barrier publishes it), instead of 6 threads x 15 x CL stores
+            constexpr int NF4 = (NWP + 4) / 4;
+            const float4* src = reinterpret_cast<const float4*>(lbuf);
+            for (int e = tid; e < NF4 * (CL - 1); e += THREADS) {
+              const int cc = e / NF4, off = e - cc * NF4;
+              int dst = rank + 1 + cc;
+              if (dst >= CL) dst -= CL;
+              reinterpret_cast<float4*>(r_row[dst] + boff + j * (NWP + 4))[off] = src[off];
+            }
+          }
+          if (is_row) apply_pivot(&s_row[0][0][0] + boff + j * (NWP + 4), k);
+        }
+        cluster.sync();
+      } else {
+        cluster.sync();
+        if (is_row) {
+          for (int j = 0; j < NB; ++j) apply_pivot(&s_row[0][0][0] + boff + j * (NWP + 4), k0 + j);
         }
       }
     }

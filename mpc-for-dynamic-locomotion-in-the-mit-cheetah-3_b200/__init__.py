@@ -12,3 +12,4 @@ from .solver import BatchedMPC, MPC, SolveStats                 # noqa: F401
 __version__ = "0.1.0"
 from . import sharding                                           # noqa: F401,E402
 from .rollout import ClosedLoopRollout                           # noqa: F401,E402
+from . import logexport                                          # noqa: F401,E402

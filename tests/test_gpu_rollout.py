@@ -132,3 +132,29 @@ def test_rollout_graph_equals_eager_and_stays_upright():
     assert sa["rms_pos_err"] < 0.05
     # warm start pays: fewer iterations per tick than a cold solve (~27-33 on mixed gaits)
     assert sa["mean_iters"] < 25
+
+
+def test_log_export_has_the_reference_schema(tmp_path, gold):
+    """The exported pickle has the keys / shapes of the reference's simulation_log.pkl
+    (reference src/logger.py:21-46) - checked by running this repo's own fixture extractor's
+    field accesses on it."""
+    import pickle
+    ro = pkg.ClosedLoopRollout(8, N=10, seed=1)
+    path = tmp_path / "simulation_log.pkl"
+    log = pkg.logexport.rollout_log(ro, 85, robot=3, path=str(path))
+    log = pickle.load(open(path, "rb"))
+    assert set(log) == {"mpc_freq", "sim_params", "total_sim_steps", "time array", "FEET POS",
+                        "MPC PREDICTIONS", "TRACKING PERFORMANCE", "FORCES", "CONTROL EFFORT"}
+    assert log["total_sim_steps"] == 85 and log["time array"] == list(range(85))
+    state = np.array(log["TRACKING PERFORMANCE"]["actual"])
+    desired = np.array(log["TRACKING PERFORMANCE"]["desired"])
+    assert state.shape == desired.shape == (85, 12)
+    forces = np.stack([np.stack([np.array(log["FORCES"][l][c]) for c in "xyz"], 1) for l in pkg.LEGS], 1)
+    assert forces.shape == (85, 4, 3) and np.all(forces[:, :, 2] >= -1e-6)
+    assert [p["time step"] for p in log["MPC PREDICTIONS"]] == [0, 80]
+    p0 = log["MPC PREDICTIONS"][0]
+    assert p0["predicted_state"].shape == (12, 11) and p0["desired_state"].shape == (12, 11)
+    assert p0["predicted forces"].shape == (4, 10)
+    assert set(log["sim_params"]) >= {"g", "h", "ss_duration", "ds_duration", "first_swing", "µ", "N",
+                                      "v_com_ref", "theta_dot", "total_steps", "world_time_step"}
+    assert log["mpc_freq"] > 1000.0          # solves per second of the single robot's tick

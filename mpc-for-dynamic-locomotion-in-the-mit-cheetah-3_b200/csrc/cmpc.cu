@@ -251,7 +251,9 @@ int cmpc_default_config(cmpc_config* cfg, int32_t N, int32_t max_batch) {
   cfg->r_weight = 0.0f;                 // src/mpc.py:121
   cfg->f_min = 3.0f;                    // src/mpc.py:45-46
   cfg->f_max = 100.0f;
-  cfg->rho = 0.3f;
+  // rho_0 follows the scale of H, which grows with the horizon (measured on the Lite3
+  // workloads: 0.5 is best at N=10, 1-3 at N=30, 2-8 at N=60)
+  cfg->rho = 0.05f * (float)N;
   cfg->sigma = 1e-6f;
   cfg->alpha = 1.6f;
   cfg->eps_abs = 1e-3f;                 // OSQP defaults (reference keeps them)
@@ -261,9 +263,9 @@ int cmpc_default_config(cmpc_config* cfg, int32_t N, int32_t max_batch) {
   cfg->refresh_every = 5;
   cfg->warm_mode = CMPC_WARM_PRIMAL;
   cfg->adaptive_rho_interval = 25;      // OSQP adapts rho too (adaptive_rho = 1 by default)
-  cfg->adaptive_rho_tolerance = 2.0f;
-  cfg->rho_min = 0.05f;                 // fp32 Woodbury form loses accuracy for rho << |H|
-  cfg->rho_max = 30.0f;
+  cfg->adaptive_rho_tolerance = 3.0f;
+  cfg->rho_min = 0.1f * cfg->rho;       // fp32 Woodbury form loses accuracy for rho << |H|
+  cfg->rho_max = 300.0f;                // problems with far-away duals want rho ~ 100
   cfg->lpt_schedule = 1024;             // hardest-first launch order for batches >= this size
   cfg->device = 0;
   return CMPC_OK;

@@ -22,7 +22,7 @@ def test_cluster_kernel_iterate_parity(N, variant, gaits):
     assert np.all(out["iters"] == K)
     for b in range(B):
         x0, r, stance, xd, mu = pb.problem(b)
-        ref = ca.solve_problem(x0, r, stance, xd, mu, DT, fixed_iters=K, rho=0.3)
+        ref = ca.solve_problem(x0, r, stance, xd, mu, DT, fixed_iters=K, rho=float(out["mpc"].cfg.rho))
         err = np.abs(out["U"][b] - ref["U"])
         # transient comparison: the fp32 Woodbury step error grows with the horizon (kappa ~ N^2)
         tr = (3e-3 if N < 60 else 6e-3) * np.abs(ref["U"]).max()

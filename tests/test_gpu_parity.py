@@ -40,6 +40,12 @@ def gpu_solve(pb, want_X=True, **opts):
     return out
 
 
+def solver_defaults(N):
+    """cmpc_default_config's ADMM settings, for the fp64 oracle."""
+    rho = 0.05 * N
+    return dict(rho=rho, adaptive_interval=25, adaptive_tolerance=3.0, rho_lim=(0.1 * rho, 300.0))
+
+
 def oracle_fixed(pb, b, K, mpc, **kw):
     x0, r, stance, xd, mu = pb.problem(b)
     return ca.solve_problem(x0, r, stance, xd, mu, DT, fixed_iters=K, rho=float(mpc.cfg.rho),
@@ -156,7 +162,7 @@ def test_tight_parity_unique_quantities():
     for b in range(pb.B):
         x0, r, stance, xd, mu = pb.problem(b)
         tight = ca.solve_problem(x0, r, stance, xd, mu, DT, tight=True, rho=0.3,
-                                 adaptive_interval=25, adaptive_tolerance=2.0)
+                                 adaptive_interval=25, adaptive_tolerance=3.0, rho_lim=(0.05, 300.0))
         if tight["status"] != 1 or tight["iters"] > 1500:
             continue            # ADMM itself needs more iterations on this problem
         ok += 1
@@ -180,7 +186,7 @@ def test_tight_parity_forces_with_force_weight():
     for b in range(pb.B):
         x0, r, stance, xd, mu = pb.problem(b)
         tight = ca.solve_problem(x0, r, stance, xd, mu, DT, tight=True, rho=0.3, r_weight=rw,
-                                 adaptive_interval=25, adaptive_tolerance=2.0)
+                                 adaptive_interval=25, adaptive_tolerance=3.0, rho_lim=(0.05, 300.0))
         if tight["status"] != 1 or tight["iters"] > 2000:
             continue
         ok += 1
@@ -387,8 +393,7 @@ def test_mpc_dropin_on_golden_states(gold):
         H, g, Sc, c0, idx = srbd_qp.condensed_qp(np.float32(x0).astype(float), np.float32(r).astype(float),
                                                  stance, np.float32(xdes).astype(float), 0.01)
         xw = None if warm is None else np.concatenate([warm[i, 3 * l:3 * l + 3] for (i, l) in idx])
-        ref = ca.admm(H, g, 1.0, rho=0.3, check_every=5, x=xw, adaptive_interval=25,
-                      adaptive_tolerance=2.0)
+        ref = ca.admm(H, g, 1.0, check_every=5, x=xw, **solver_defaults(10))
         U = np.zeros((10, 12))
         for s, (i, l) in enumerate(idx):
             U[i, 3 * l:3 * l + 3] = ref["x"][3 * s:3 * s + 3]

@@ -103,7 +103,8 @@ def test_closed_loop_matches_fp64_loop():
         for b in range(B):
             H, g, Sc, c0, idx = srbd_qp.condensed_qp(x[b], r[b], stance[b], xd[b].T, DT)
             xw = None if warm[b] is None else np.concatenate([warm[b][i, 3 * l:3 * l + 3] for (i, l) in idx])
-            res = ca.admm(H, g, mu[b], rho=0.3, check_every=5, x=xw, adaptive_interval=25, adaptive_tolerance=2.0)
+            res = ca.admm(H, g, mu[b], check_every=5, x=xw, rho=0.5, adaptive_interval=25,
+                          adaptive_tolerance=3.0, rho_lim=(0.05, 300.0))
             U = np.zeros((10, 12))
             for s_, (i, l) in enumerate(idx):
                 U[i, 3 * l:3 * l + 3] = res["x"][3 * s_:3 * s_ + 3]

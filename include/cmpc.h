@@ -161,6 +161,10 @@ int cmpc_plant_step(cmpc_handle* h, int32_t B, const cmpc_gait_tables* gt, int32
                     float* x, const float* r, const float* U, const float* x_des,
                     float* yaw_start, float* com_start, float* track_err, void* stream);
 
+/* Measures the FP32 FMA throughput of `device` (TFLOP/s, best of 4 timed launches of an 8-chain
+ * FMA kernel): the denominator of the on-chip roofline of the solve kernel. */
+int cmpc_fp32_peak(int32_t device, float* tflops);
+
 /* Number of kernels this library has launched on behalf of `h` since creation. */
 int64_t cmpc_launch_count(const cmpc_handle* h);
 

@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 SYMBOLS = ("cmpc_default_config", "cmpc_create", "cmpc_destroy", "cmpc_solve", "cmpc_solve_host",
            "cmpc_condense", "cmpc_reset_warm", "cmpc_get_warm", "cmpc_set_warm",
            "cmpc_launch_count", "cmpc_supported_horizons", "cmpc_version", "cmpc_last_error",
-           "cmpc_assemble", "cmpc_plant_step")
+           "cmpc_assemble", "cmpc_plant_step", "cmpc_fp32_peak")
 
 
 class CmpcError(RuntimeError):
@@ -104,6 +104,7 @@ def lib() -> C.CDLL:
     gtp = C.POINTER(GaitTables)
     L.cmpc_assemble.argtypes = [vp, i32, gtp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.cmpc_plant_step.argtypes = [vp, i32, gtp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.cmpc_fp32_peak.argtypes = [i32, C.POINTER(C.c_float)]
     L.cmpc_launch_count.argtypes = [vp]
     L.cmpc_launch_count.restype = C.c_int64
     L.cmpc_supported_horizons.argtypes = [C.POINTER(C.c_int32), i32]
@@ -125,6 +126,13 @@ def default_config(N: int, max_batch: int) -> Config:
     cfg = Config()
     check(lib().cmpc_default_config(C.byref(cfg), N, max_batch))
     return cfg
+
+
+def fp32_peak(device=0) -> float:
+    """Measured FP32 FMA peak of `device` in TFLOP/s."""
+    v = C.c_float()
+    check(lib().cmpc_fp32_peak(device, C.byref(v)))
+    return float(v.value)
 
 
 def supported_horizons():

@@ -489,6 +489,41 @@ int cmpc_plant_step(cmpc_handle* h, int32_t B, const cmpc_gait_tables* gt, int32
   return CMPC_OK;
 }
 
+int cmpc_fp32_peak(int32_t device, float* tflops) {
+  if (!tflops) return fail(CMPC_ERR_INVALID, "null pointer");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(CMPC_ERR_NO_DEVICE, "no CUDA device visible");
+  }
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop{};
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  const int grid = prop.multiProcessorCount * 8, iters = 4096;
+  float* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, (size_t)grid * 256 * sizeof(float)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  float best = 0.f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0));
+    cmpc::fma_peak_kernel<<<grid, 256>>>(d, iters, 0.999f, 0.001f);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double flop = 2.0 * 64.0 * iters * 256.0 * grid;
+    const float tf = (float)(flop / (ms * 1e-3) / 1e12);
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return CMPC_OK;
+}
+
 // ---- host-buffer path -------------------------------------------------------------------
 namespace {
 struct Layout {   // byte offsets of one chunk of C problems inside the in/out arenas

@@ -170,6 +170,7 @@ solve_kernel(const SolveParams p) {
   __shared__ __align__(16) float s_h[NWP];             // linear term h
   __shared__ __align__(16) float s_S[NWP];             // Jacobi scaling 1/sqrt(P_ii) of the sweep
   __shared__ float s_red[2][LWARPS][8];
+  __shared__ float s_pre[2][6 * (N + 1)];              // prefix sums for the X output
   __shared__ int s_mask[N];
 
   if ((int)blockIdx.x >= p.B) return;
@@ -604,6 +605,21 @@ solve_kernel(const SolveParams p) {
         *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = make_float2(wv[2 * ll], wv[2 * ll + 1]);
     }
     __syncthreads();
+    // prefix sums of the wrench sequence per axis: c1[k] = sum_{j<k} w_j, c2[k] = sum_{j<k} (k-1-j) w_j
+    float* c1 = &s_pre[0][0];            // [6][N+1]
+    float* c2 = &s_pre[1][0];
+    if (tid < 6) {
+      float a1 = 0.f, a2 = 0.f;
+      c1[tid * (N + 1)] = 0.f;
+      c2[tid * (N + 1)] = 0.f;
+      for (int k = 1; k <= N; ++k) {
+        a2 += a1;
+        a1 += s_s[6 * (k - 1) + tid];
+        c1[tid * (N + 1) + k] = a1;
+        c2[tid * (N + 1) + k] = a2;
+      }
+    }
+    __syncthreads();
     const float dt = p.dt, g = s_x0[12];
     for (int o = tid; o < NX; o += THREADS) {
       const int k = o / 13, cidx = o % 13;
@@ -614,26 +630,19 @@ solve_kernel(const SolveParams p) {
       } else if (cidx < 3) {           // Theta_k = Theta_0 + k d Rz w0 + d^2 sum (k-1-j) tau^_j
         const float rw0 = cidx == 0 ? (cs * s_x0[6] - sn * s_x0[7])
                                     : (cidx == 1 ? (sn * s_x0[6] + cs * s_x0[7]) : s_x0[8]);
-        float acc = 0.f;
-        for (int j = 0; j < k; ++j) acc += (float)(k - 1 - j) * s_s[6 * j + cidx];
-        val = s_x0[cidx] + kf * dt * rw0 + dt * dt * acc;
+        val = s_x0[cidx] + kf * dt * rw0 + dt * dt * c2[cidx * (N + 1) + k];
       } else if (cidx < 6) {           // p_k
         const int aa = cidx - 3;
-        float acc = 0.f;
-        for (int j = 0; j < k; ++j) acc += (float)(k - 1 - j) * s_s[6 * j + 3 + aa];
-        val = s_x0[cidx] + kf * dt * s_x0[9 + aa] + dt * dt * acc;
+        val = s_x0[cidx] + kf * dt * s_x0[9 + aa] + dt * dt * c2[(3 + aa) * (N + 1) + k];
         if (aa == 2) val += 0.5f * kf * (kf - 1.f) * dt * dt * g;
       } else if (cidx < 9) {           // omega_k = omega_0 + d Rz' sum tau^_j
-        float sx = 0.f, sy = 0.f, sz = 0.f;
-        for (int j = 0; j < k; ++j) { sx += s_s[6 * j]; sy += s_s[6 * j + 1]; sz += s_s[6 * j + 2]; }
+        const float sx = c1[k], sy = c1[(N + 1) + k], sz = c1[2 * (N + 1) + k];
         const int aa = cidx - 6;
         const float rot = aa == 0 ? (cs * sx + sn * sy) : (aa == 1 ? (-sn * sx + cs * sy) : sz);
         val = s_x0[cidx] + dt * rot;
       } else {                         // v_k
         const int aa = cidx - 9;
-        float acc = 0.f;
-        for (int j = 0; j < k; ++j) acc += s_s[6 * j + 3 + aa];
-        val = s_x0[cidx] + dt * acc;
+        val = s_x0[cidx] + dt * c1[(3 + aa) * (N + 1) + k];
         if (aa == 2) val += kf * dt * g;
       }
       p.X[(size_t)b * NX + o] = val;
@@ -954,5 +963,20 @@ __global__ void __launch_bounds__(128) plant_kernel(const PlantParams p) {
 }
 
 __global__ void tick_kernel(int32_t* tick) { *tick += 1; }
+
+// FP32 FMA micro-benchmark: the denominator of the on-chip roofline.
+// 8 independent FMA chains per thread, 256 threads, grid = a multiple of the SM count.
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b) {
+  float v0 = threadIdx.x, v1 = v0 + 1.f, v2 = v0 + 2.f, v3 = v0 + 3.f, v4 = v0 + 4.f, v5 = v0 + 5.f,
+        v6 = v0 + 6.f, v7 = v0 + 7.f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      v0 = fmaf(v0, a, b); v1 = fmaf(v1, a, b); v2 = fmaf(v2, a, b); v3 = fmaf(v3, a, b);
+      v4 = fmaf(v4, a, b); v5 = fmaf(v5, a, b); v6 = fmaf(v6, a, b); v7 = fmaf(v7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+}
 
 }  // namespace cmpc

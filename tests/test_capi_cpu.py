@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_header_symbols_are_exported():
     hdr = open(os.path.join(ROOT, "include", "cmpc.h")).read()
-    declared = set(re.findall(r"\b(cmpc_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(cmpc_[a-z0-9_]+)\s*\(", hdr))
     declared -= {"cmpc_config", "cmpc_handle"}
     assert declared == set(_capi.SYMBOLS)
     L = _capi.lib()

@@ -85,6 +85,10 @@ typedef struct cmpc_config {
   int32_t lpt_schedule; /* >0: batches of at least this size are launched hardest-first
                            (conditioning score), 0 = launch in batch order               */
   int32_t device;       /* CUDA device ordinal                                       */
+  int32_t host_zero_copy; /* cmpc_solve_host with page-locked caller buffers: 1 = the solve kernel
+                           reads the inputs and writes the results directly in host memory over
+                           PCIe (no staging copies, transfers overlap the solve CTA by CTA);
+                           0 = chunked cudaMemcpyAsync pipeline                              */
 } cmpc_config;
 
 typedef struct cmpc_handle cmpc_handle;
@@ -106,8 +110,10 @@ int cmpc_solve(cmpc_handle* h, int32_t B, int32_t slot0,
                const float* mu, float* U, float* X, int32_t* iters, float* pri_res,
                float* dua_res, int32_t* status, void* stream);
 
-/* Same call with HOST pointers: stages through pinned buffers, overlaps H2D / solve / D2H
- * in chunks on internal streams and returns when the outputs are in host memory.
+/* Same call with HOST pointers; returns when the outputs are in host memory.  Page-locked
+ * (cudaHostAlloc / torch pin_memory) buffers are accessed by the kernel in place when
+ * cfg.host_zero_copy is set; otherwise, and for pageable buffers, the batch is staged through
+ * pinned arenas in two chunks so that H2D / solve / D2H overlap on internal streams.
  * This is the call the reference-facing Python `MPC.solve` drop-in makes. */
 int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0,
                     const float* x0, const float* r, const uint8_t* mask, const float* x_des,

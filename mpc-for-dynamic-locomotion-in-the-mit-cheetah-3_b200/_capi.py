@@ -45,7 +45,7 @@ class Config(C.Structure):
                 ("adaptive_rho_interval", C.c_int32), ("adaptive_rho_tolerance", C.c_float),
                 ("rho_min", C.c_float), ("rho_max", C.c_float),
                 ("kernel_variant", C.c_int32), ("lpt_schedule", C.c_int32),
-                ("device", C.c_int32)]
+                ("device", C.c_int32), ("host_zero_copy", C.c_int32)]
 
 
 class GaitTables(C.Structure):

@@ -127,7 +127,7 @@ cudaError_t launch_condense(const cmpc::CondenseParams& p, cudaStream_t s) {
 
 struct HorizonEntry {
   int N;
-  SolveLaunch solve[3];      // thread-layout variants (nullptr = not compiled)
+  SolveLaunch solve[5];      // thread-layout variants (nullptr = not compiled)
   CondenseLaunch condense;
   ScoreLaunch score;
   AssembleLaunch assemble;
@@ -139,11 +139,11 @@ const HorizonEntry kHorizons[] = {
     {4, {launch_solve<4, 1, 8>, nullptr, nullptr}, launch_condense<4>, launch_score<4>, launch_assemble<4>},
     {5, {launch_solve<5, 1, 8>, nullptr, nullptr}, launch_condense<5>, launch_score<5>, launch_assemble<5>},
     {8, {launch_solve<8, 1, 8>, nullptr, nullptr}, launch_condense<8>, launch_score<8>, launch_assemble<8>},
-    {10, {launch_solve<10, 1, 8>, launch_solve<10, 2, 4>, launch_solve<10, 4, 2>}, launch_condense<10>, launch_score<10>, launch_assemble<10>},
+    {10, {launch_solve<10, 1, 8>, launch_solve<10, 2, 4>, launch_solve<10, 4, 2>, launch_solve<10, 1, 10>, launch_solve<10, 2, 6>}, launch_condense<10>, launch_score<10>, launch_assemble<10>},
     {12, {launch_solve<12, 2, 4>, nullptr, nullptr}, launch_condense<12>, launch_score<12>, launch_assemble<12>},
     {16, {launch_solve<16, 2, 3>, nullptr, nullptr}, launch_condense<16>, launch_score<16>, launch_assemble<16>},
     {20, {launch_solve<20, 2, 2>, launch_solve<20, 3, 1>, launch_solve_cluster<10, 2, 2, 3>}, launch_condense<20>, launch_score<20>, launch_assemble<20>},
-    {30, {launch_solve<30, 3, 1>, launch_solve<30, 4, 1>, launch_solve_cluster<10, 3, 3, 2>}, launch_condense<30>, launch_score<30>, launch_assemble<30>},
+    {30, {launch_solve<30, 3, 1>, launch_solve<30, 4, 1>, launch_solve_cluster<10, 3, 3, 2>, launch_solve<30, 2, 1>, nullptr}, launch_condense<30>, launch_score<30>, launch_assemble<30>},
     {40, {launch_solve_cluster<10, 4, 4, 1>, nullptr, nullptr}, nullptr, launch_score<40>, launch_assemble<40>},
     {60, {launch_solve_cluster<10, 6, 6, 1>, nullptr, nullptr}, nullptr, launch_score<60>, launch_assemble<60>},
 };
@@ -156,7 +156,7 @@ const HorizonEntry* find_horizon(int N) {
 
 SolveLaunch pick_solve(const cmpc_config& c) {
   const HorizonEntry* e = find_horizon(c.N);
-  const int v = (c.kernel_variant >= 0 && c.kernel_variant < 3) ? c.kernel_variant : 0;
+  const int v = (c.kernel_variant >= 0 && c.kernel_variant < 5) ? c.kernel_variant : 0;
   return e->solve[v] ? e->solve[v] : e->solve[0];
 }
 
@@ -268,6 +268,7 @@ int cmpc_default_config(cmpc_config* cfg, int32_t N, int32_t max_batch) {
   cfg->rho_max = 300.0f;                // problems with far-away duals want rho ~ 100
   cfg->lpt_schedule = 1024;             // hardest-first launch order for batches >= this size
   cfg->device = 0;
+  cfg->host_zero_copy = 1;              // pinned caller buffers are accessed in place
   return CMPC_OK;
 }
 
@@ -553,15 +554,19 @@ Layout make_layout(int N, int C, bool withX) {
 }  // namespace
 
 namespace {
-// true if `ptr` is page-locked host memory the DMA engines can read/write directly
-bool is_pinned(const void* ptr) {
+// true if `ptr` is page-locked host memory the DMA engines can read/write directly;
+// *dev (optional) receives the address under which kernels on the current device see it
+bool is_pinned(const void* ptr, void** dev = nullptr) {
+  if (dev) *dev = nullptr;
   if (!ptr) return true;
   cudaPointerAttributes at{};
   if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
     cudaGetLastError();
     return false;
   }
-  return at.type == cudaMemoryTypeHost;
+  if (at.type != cudaMemoryTypeHost) return false;
+  if (dev) *dev = at.devicePointer;
+  return true;
 }
 }  // namespace
 
@@ -575,6 +580,34 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, c
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   const int N = h->cfg.N;
   Staging& st = h->st;
+  if (h->cfg.host_zero_copy) {
+    // Page-locked caller buffers: one launch over the whole batch, every CTA pulls its own
+    // ~1.1 KB record over PCIe and pushes its results back, so the transfers overlap the
+    // solve CTA by CTA and no copy is ever enqueued.  All accesses of the kernel to these
+    // buffers are coalesced and touch every byte once.
+    void *dx0, *dr, *dmask, *dxd, *dmu, *dU, *dX, *dit, *dpr, *ddu, *dst;
+    const bool ok = is_pinned(x0, &dx0) && is_pinned(r, &dr) && is_pinned(mask, &dmask) &&
+                    is_pinned(x_des, &dxd) && is_pinned(mu, &dmu) && is_pinned(U, &dU) &&
+                    is_pinned(X, &dX) && is_pinned(iters, &dit) && is_pinned(pri_res, &dpr) &&
+                    is_pinned(dua_res, &ddu) && is_pinned(status, &dst);
+    if (ok && dx0 && dr && dmask && dxd && dmu && dU) {
+      if (!st.streams[0]) CUDA_TRY(cudaStreamCreateWithFlags(&st.streams[0], cudaStreamNonBlocking));
+      cmpc::SolveParams p{};
+      fill_solve_params(h, p);
+      p.x0 = (const float*)dx0; p.r = (const float*)dr; p.mask = (const uint8_t*)dmask;
+      p.x_des = (const float*)dxd; p.mu = (const float*)dmu;
+      p.U = (float*)dU; p.X = (float*)dX; p.iters = (int32_t*)dit; p.pri_res = (float*)dpr;
+      p.dua_res = (float*)ddu; p.status = (int32_t*)dst;
+      p.B = B;
+      p.slot0 = slot0;
+      rc = schedule_batch(h, p, 0, 0, st.streams[0]);
+      if (rc) return rc;
+      CUDA_TRY(pick_solve(h->cfg)(p, st.streams[0]));
+      h->launches.fetch_add(1);
+      CUDA_TRY(cudaStreamSynchronize(st.streams[0]));
+      return CMPC_OK;
+    }
+  }
   // Two chunks on two streams: H2D(1) overlaps solve(0), D2H(0) overlaps solve(1).  More
   // chunks would give every chunk its own straggler tail.
   const int nchunk = B >= 2048 ? 2 : 1;

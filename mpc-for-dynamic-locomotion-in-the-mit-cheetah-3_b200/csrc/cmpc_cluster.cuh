@@ -332,7 +332,7 @@ solve_cluster_kernel(const SolveParams p) {
       for (int k = 0; k < 3; ++k) wv[3 + k] = quad_sum(v3[k] * im);
       if (is_leg && ll < 3) {
         const int off = (ag & 1) * NWP + 6 * (j0 + lj) + 2 * ll;
-        const float2 val = make_float2(wv[2 * ll], wv[2 * ll + 1]);
+        const float2 val = pick_pair(wv, ll);
 #pragma unroll
         for (int c = 0; c < CL; ++c) *reinterpret_cast<float2*>(r_s[c] + off) = val;
       }

@@ -77,6 +77,12 @@ __device__ __forceinline__ float quad_sum(float v) {
   return v;
 }
 
+// (a[2l], a[2l+1]) for l = 0..2 by selects: a dynamically indexed register array would be
+// demoted to local memory (a store + load round trip per ADMM iteration)
+__device__ __forceinline__ float2 pick_pair(const float a[6], int l) {
+  return make_float2(l == 0 ? a[0] : (l == 1 ? a[2] : a[4]), l == 0 ? a[1] : (l == 1 ? a[3] : a[5]));
+}
+
 __device__ __forceinline__ float warp_max_nonneg(float v) {
   // v >= 0 (or NaN): IEEE bit patterns of non-negative floats order like unsigned ints,
   // NaN (0x7fc00000) sorts above every finite value so it propagates.
@@ -161,7 +167,8 @@ solve_kernel(const SolveParams p) {
   constexpr int THREADS = G_::THREADS, LWARPS = G_::LWARPS, NX = G_::NX;
 
   __shared__ __align__(16) float s_x0[16];
-  __shared__ __align__(16) float s_xd[NX + 3];
+  __shared__ __align__(16) float s_xd[NX + 3];         // x_des; reused to stage U at the end
+  __shared__ __align__(16) float s_r[3 * NLEG];        // lever arms as loaded (coalesced)
   __shared__ __align__(16) float s_G[NLEG][12];        // Ghat (9) + dxy, dz, pad per leg
   __shared__ __align__(16) float s_row[2][NWP + 4];    // pivot-row double buffer (+ 1/pivot)
   __shared__ __align__(16) float s_s[NWP];             // wrench-space rhs  s = G D^-1 b
@@ -180,21 +187,20 @@ solve_kernel(const SolveParams p) {
   const bool leg_warp = warp < LWARPS;   // warp-uniform: warps without leg threads skip leg phases
   const int slot = p.slot0 + b;
 
-  // ---- phase 0: stage the per-problem record (coalesced 4-byte loads) -------------------
+  // ---- phase 0: stage the per-problem record (coalesced 4-byte loads, every byte requested
+  // once: the record may live in page-locked HOST memory, see cmpc_solve_host) --------------
   for (int i = tid; i < 13; i += THREADS) s_x0[i] = __ldg(p.x0 + (size_t)b * 13 + i);
   for (int i = tid; i < NX; i += THREADS) s_xd[i] = __ldg(p.x_des + (size_t)b * NX + i);
+  for (int i = tid; i < 3 * NLEG; i += THREADS) s_r[i] = __ldg(p.r + (size_t)b * 3 * NLEG + i);
   for (int i = tid; i < N; i += THREADS) s_mask[i] = (int)__ldg(p.mask + (size_t)b * N + i);
   for (int i = tid; i < NWP; i += THREADS) { s_s[i] = 0.f; s_v[i] = 0.f; s_h[i] = 0.f; s_S[i] = 0.f; }
   const float mu = __ldg(p.mu + b);
   // issue every other global load of this problem now so that their DRAM latencies overlap
   const bool is_leg = tid < NLEG;
-  float r_in[3] = {0.f, 0.f, 0.f};
   float wx_in[3] = {0.f, 0.f, 0.f};
   float wy_in[3] = {0.f, 0.f, 0.f};
   const bool warm = p.warm_mode != 0 && p.warm_valid[slot] != 0;
   if (is_leg) {
-    const float* rp = p.r + ((size_t)b * NLEG + tid) * 3;
-    r_in[0] = __ldg(rp); r_in[1] = __ldg(rp + 1); r_in[2] = __ldg(rp + 2);
     if (warm) {
       const float* wx = p.warm_x + ((size_t)slot * NLEG + tid) * 3;
       wx_in[0] = wx[0]; wx_in[1] = wx[1]; wx_in[2] = wx[2];
@@ -224,7 +230,7 @@ solve_kernel(const SolveParams p) {
     for (int k = 0; k < 3; ++k) Gh[a][k] = 0.f;
   if (is_leg) {
     stance = (s_mask[lj] >> ll) & 1;
-    leg_map(cs, sn, p.ib, r_in[0], r_in[1], r_in[2], Gh);
+    leg_map(cs, sn, p.ib, s_r[3 * tid], s_r[3 * tid + 1], s_r[3 * tid + 2], Gh);
     if (!stance) {
 #pragma unroll
       for (int a = 0; a < 3; ++a)
@@ -404,7 +410,7 @@ solve_kernel(const SolveParams p) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) wv[3 + k] = quad_sum(x[k] * im);
       if (is_leg && ll < 3)
-        *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = make_float2(wv[2 * ll], wv[2 * ll + 1]);
+        *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = pick_pair(wv, ll);
     }
     __syncthreads();
     if (is_row && rs == 0) {
@@ -475,7 +481,7 @@ solve_kernel(const SolveParams p) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) sv[3 + k] = quad_sum(t[k] * im);
       if (is_leg && ll < 3)
-        *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = make_float2(sv[2 * ll], sv[2 * ll + 1]);
+        *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = pick_pair(sv, ll);
       if (chk) {
         float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, sum = 0.f;
         if (stance) {
@@ -577,8 +583,7 @@ solve_kernel(const SolveParams p) {
 
   // ---- phase 6: outputs -----------------------------------------------------------------------
   if (is_leg) {
-    float* up = p.U + ((size_t)b * NLEG + tid) * 3;
-    up[0] = x[0]; up[1] = x[1]; up[2] = x[2];
+    s_xd[3 * tid] = x[0]; s_xd[3 * tid + 1] = x[1]; s_xd[3 * tid + 2] = x[2];   // staged, stored below
     float* wx = p.warm_x + ((size_t)slot * NLEG + tid) * 3;
     wx[0] = x[0]; wx[1] = x[1]; wx[2] = x[2];
     float* wy = p.warm_y + ((size_t)slot * NLEG + tid) * 3;
@@ -591,6 +596,8 @@ solve_kernel(const SolveParams p) {
     if (p.status) p.status[b] = status;
     p.warm_valid[slot] = status >= 0 ? 1 : 0;
   }
+  __syncthreads();
+  for (int i = tid; i < 3 * NLEG; i += THREADS) p.U[(size_t)b * 3 * NLEG + i] = s_xd[i];
   if (p.X) {
     // predicted states X = free response + forced response of the wrench sequence w = G x
     __syncthreads();
@@ -602,7 +609,7 @@ solve_kernel(const SolveParams p) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) wv[3 + k] = quad_sum(x[k] * im);
       if (is_leg && ll < 3)
-        *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = make_float2(wv[2 * ll], wv[2 * ll + 1]);
+        *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = pick_pair(wv, ll);
     }
     __syncthreads();
     // prefix sums of the wrench sequence per axis: c1[k] = sum_{j<k} w_j, c2[k] = sum_{j<k} (k-1-j) w_j
@@ -690,11 +697,16 @@ __global__ void __launch_bounds__(128) score_kernel(const ScoreParams p) {
     float md[6];
 #pragma unroll
     for (int a = 0; a < 6; ++a) md[a] = __ldg(p.Mg + ((size_t)a * N + j) * N + j);
+    // the stage's 12 lever-arm floats as three 16-byte loads (48 B records are 16-B aligned);
+    // few, wide requests also when the batch is read in place from page-locked host memory
+    const float4* rq = reinterpret_cast<const float4*>(p.r + ((size_t)b * N + j) * 12);
+    const float4 q0 = __ldg(rq), q1 = __ldg(rq + 1), q2 = __ldg(rq + 2);
+    const float rr[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
     for (int l = 0; l < 4; ++l) {
       if (!((m >> l) & 1)) continue;
-      const float* rp = p.r + (((size_t)b * N + j) * 4 + l) * 3;
       float G[3][3];
-      leg_map(cs, sn, p.ib, __ldg(rp), __ldg(rp + 1), __ldg(rp + 2), G);
+      leg_map(cs, sn, p.ib, rr[3 * l], rr[3 * l + 1], rr[3 * l + 2], G);
 #pragma unroll
       for (int c = 0; c < 3; ++c)
         acc += G[0][c] * G[0][c] * md[0] + G[1][c] * G[1][c] * md[1] + G[2][c] * G[2][c] * md[2] +

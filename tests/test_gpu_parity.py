@@ -254,10 +254,27 @@ def test_host_path_matches_device_path_and_sharding():
     pb = synthetic_batch(2500, N=10, gaits=GAIT_NAMES, seed=9)
     d = gpu_solve(pb, warm_mode=0)
     mpc = pkg.BatchedMPC(N=10, max_batch=pb.B, warm_mode=0)
-    U, X, st = mpc.solve_host(*pb.f32())
+    U, X, st = mpc.solve_host(*pb.f32())          # pageable buffers: staged through pinned arenas
     assert np.array_equal(U.astype(np.float64), d["U"])
     assert np.array_equal(X.astype(np.float64), d["X"])
     assert np.array_equal(st.iters, d["iters"]) and np.array_equal(st.status, d["status"])
+    # page-locked caller buffers: (1) read / written in place by the kernel over PCIe (default),
+    # (0) chunked cudaMemcpyAsync pipeline - both bit-identical to the device path
+    hin = [torch.from_numpy(a).pin_memory().numpy() for a in pb.f32()]
+    pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()
+    for zero_copy in (1, 0):
+        m2 = pkg.BatchedMPC(N=10, max_batch=pb.B, warm_mode=0, host_zero_copy=zero_copy)
+        hout = (pin((pb.B, 10, 12), torch.float32), pin((pb.B, 11, 13), torch.float32),
+                pin((pb.B,), torch.int32), pin((pb.B,), torch.float32), pin((pb.B,), torch.float32),
+                pin((pb.B,), torch.int32))
+        Uh, Xh, sh = m2.solve_host(*hin, out=hout)
+        assert np.array_equal(Uh.astype(np.float64), d["U"]), zero_copy
+        assert np.array_equal(Xh.astype(np.float64), d["X"]), zero_copy
+        assert np.array_equal(sh.iters, d["iters"]) and np.array_equal(sh.status, d["status"])
+        # optional outputs may be NULL
+        U3, X3, s3 = m2.solve_host(*hin, want_X=False,
+                                   out=(hout[0], None, hout[2], hout[3], hout[4], hout[5]))
+        assert X3 is None and np.array_equal(U3.astype(np.float64), d["U"])
     h = pb.B // 2
     a = gpu_solve(pb.slice(0, h), warm_mode=0)
     b = gpu_solve(pb.slice(h, pb.B), warm_mode=0)

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -86,9 +87,9 @@ using CondenseLaunch = cudaError_t (*)(const cmpc::CondenseParams&, cudaStream_t
 using ScoreLaunch = cudaError_t (*)(const cmpc::ScoreParams&, cudaStream_t);
 using AssembleLaunch = cudaError_t (*)(const cmpc::AssembleParams&, cudaStream_t);
 
-template <int N, int SPLIT, int MINB>
+template <int N, int SPLIT, int MINB, int R = 1>
 cudaError_t launch_solve(const cmpc::SolveParams& p, cudaStream_t s) {
-  cmpc::solve_kernel<N, SPLIT, MINB><<<p.B, cmpc::Geo<N, SPLIT>::THREADS, 0, s>>>(p);
+  cmpc::solve_kernel<N, SPLIT, MINB, R><<<p.B, cmpc::Geo<N, SPLIT, R>::THREADS, 0, s>>>(p);
   return cudaGetLastError();
 }
 // one thread-block cluster of CL CTAs per problem (long horizons, see cmpc_cluster.cuh)
@@ -133,17 +134,20 @@ struct HorizonEntry {
   AssembleLaunch assemble;
 };
 
-// Horizons with compiled kernels.  <N, SPLIT, MINB>: SPLIT threads share one row of the
-// 6N x 6N wrench matrix so that the register-resident row slice stays <= 60 floats.
+// Horizons with compiled kernels.  <N, SPLIT, MINB, R>: a thread owns an R x (6N/SPLIT) register
+// tile of the 6N x 6N wrench matrix (R rows, one of SPLIT column slices), <= 96 floats.
+// Slot 0 is the default layout, the others are alternatives selectable with kernel_variant
+// (measured on B200: N=10 <10,1,8> 12.1 M solves/s vs 9.5-10.7 M for the R-blocked layouts;
+// N=30 <30,6,1,3> 764 k solves/s vs 703 k for <30,3,1>).
 const HorizonEntry kHorizons[] = {
     {4, {launch_solve<4, 1, 8>, nullptr, nullptr}, launch_condense<4>, launch_score<4>, launch_assemble<4>},
     {5, {launch_solve<5, 1, 8>, nullptr, nullptr}, launch_condense<5>, launch_score<5>, launch_assemble<5>},
     {8, {launch_solve<8, 1, 8>, nullptr, nullptr}, launch_condense<8>, launch_score<8>, launch_assemble<8>},
-    {10, {launch_solve<10, 1, 8>, launch_solve<10, 2, 4>, launch_solve<10, 4, 2>, launch_solve<10, 1, 10>, launch_solve<10, 2, 6>}, launch_condense<10>, launch_score<10>, launch_assemble<10>},
+    {10, {launch_solve<10, 1, 8>, launch_solve<10, 2, 4>, launch_solve<10, 4, 2>, launch_solve<10, 2, 8, 2>, launch_solve<10, 5, 8, 5>}, launch_condense<10>, launch_score<10>, launch_assemble<10>},
     {12, {launch_solve<12, 2, 4>, nullptr, nullptr}, launch_condense<12>, launch_score<12>, launch_assemble<12>},
     {16, {launch_solve<16, 2, 3>, nullptr, nullptr}, launch_condense<16>, launch_score<16>, launch_assemble<16>},
     {20, {launch_solve<20, 2, 2>, launch_solve<20, 3, 1>, launch_solve_cluster<10, 2, 2, 3>}, launch_condense<20>, launch_score<20>, launch_assemble<20>},
-    {30, {launch_solve<30, 3, 1>, launch_solve<30, 4, 1>, launch_solve_cluster<10, 3, 3, 2>, launch_solve<30, 2, 1>, nullptr}, launch_condense<30>, launch_score<30>, launch_assemble<30>},
+    {30, {launch_solve<30, 6, 1, 3>, launch_solve<30, 3, 1>, launch_solve_cluster<10, 3, 3, 2>, launch_solve<30, 6, 1, 2>, launch_solve<30, 3, 1, 2>}, launch_condense<30>, launch_score<30>, launch_assemble<30>},
     {40, {launch_solve_cluster<10, 4, 4, 1>, nullptr, nullptr}, nullptr, launch_score<40>, launch_assemble<40>},
     {60, {launch_solve_cluster<10, 6, 6, 1>, nullptr, nullptr}, nullptr, launch_score<60>, launch_assemble<60>},
 };
@@ -202,6 +206,8 @@ int schedule_batch(cmpc_handle* h, cmpc::SolveParams& p, int order_off, int hist
   sp.B = p.B;
   sp.inv_mass = 1.0f / c.mass;
   for (int i = 0; i < 3; ++i) sp.ib[i] = c.ibody_inv[i];
+  // (one fused single-CTA score+sort kernel was measured slower than these two launches:
+  // its dependent load rounds cost more than the kernel boundary it saves)
   CUDA_TRY(find_horizon(c.N)->score(sp, s));
   cmpc::order_kernel<<<1, 1024, 0, s>>>(sp.score, sp.hist, h->d_order + order_off, p.B);
   CUDA_TRY(cudaGetLastError());
@@ -400,8 +406,17 @@ int cmpc_solve(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, const 
   p.slot0 = slot0;
   rc = schedule_batch(h, p, 0, 0, (cudaStream_t)stream);
   if (rc) return rc;
+  static const bool dbg = std::getenv("CMPC_DEBUG_CLOCKS") != nullptr;   // developer aid, synchronous
+  if (dbg) CUDA_TRY(cudaMalloc(&p.dbg_clk, 8 * sizeof(long long)));
   CUDA_TRY(pick_solve(h->cfg)(p, (cudaStream_t)stream));
   h->launches.fetch_add(1);
+  if (dbg) {
+    long long c[8];
+    CUDA_TRY(cudaMemcpy(c, p.dbg_clk, sizeof c, cudaMemcpyDeviceToHost));
+    cudaFree(p.dbg_clk);
+    std::fprintf(stderr, "cmpc clocks (CTA 0): load %lld geometry %lld P-build %lld sweep %lld init %lld admm %lld output %lld\n",
+                 c[1] - c[0], c[2] - c[1], c[3] - c[2], c[4] - c[3], c[5] - c[4], c[6] - c[5], c[7] - c[6]);
+  }
   return CMPC_OK;
 }
 

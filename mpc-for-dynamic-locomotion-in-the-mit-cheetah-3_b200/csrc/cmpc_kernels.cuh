@@ -55,21 +55,37 @@ struct SolveParams {
   int32_t adaptive_rho_interval;      // 0 = fixed rho
   float adaptive_rho_tolerance;
   float rho_min, rho_max;             // clamp of the adapted rho (fp32 stability of the Woodbury form)
+  long long* dbg_clk;                 // debug: phase timestamps of CTA 0 (nullptr in production)
 };
 
-template <int N, int SPLIT>
+// Thread geometry.  Every "row thread" owns R rows of P (rows rp + q*NWR, q < R: same axis,
+// stages N/R apart) restricted to one of SPLIT column slices, i.e. an R x COLS register tile.
+// One broadcast 16-byte shared-memory load of the pivot row / rhs feeds 4R FMAs: R = 1 makes
+// the sweep shared-memory-bandwidth bound (measured: a warp-uniform LDS.128 costs 2.4 cycles of
+// the SM's shared-memory pipe, 15 of them per 60 FMAs), R = 2 halves that traffic.
+template <int N, int SPLIT, int R = 1>
 struct Geo {
+  static_assert(N % R == 0, "rows of one thread must share their axis");
   static constexpr int NW = 6 * N;                                  // wrench dimension
+  static constexpr int NWR = NW / R;                                // row groups
   static constexpr int NWP = ((NW + 4 * SPLIT - 1) / (4 * SPLIT)) * (4 * SPLIT);
   static constexpr int COLS = NWP / SPLIT;                          // row slice per thread
   static constexpr int NLEG = 4 * N;
-  static constexpr int ROWT = NW * SPLIT;                           // threads owning P rows
+  static constexpr int ROWT = NWR * SPLIT;                          // threads owning P rows
   static constexpr int TMAX = ROWT > NLEG ? ROWT : NLEG;
   static constexpr int THREADS = ((TMAX + 31) / 32) * 32;
   static constexpr int WARPS = THREADS / 32;
   static constexpr int LWARPS = (NLEG + 31) / 32;                   // warps that own leg threads
   static constexpr int NX = 13 * (N + 1);
 };
+
+// a[i] for a runtime i by selects (a dynamically indexed register array goes to local memory)
+__device__ __forceinline__ float pick6(const float a[6], int i) {
+  float e = a[0];
+#pragma unroll
+  for (int q = 1; q < 6; ++q) e = (i == q) ? a[q] : e;
+  return e;
+}
 
 __device__ __forceinline__ float quad_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -159,11 +175,11 @@ __device__ __forceinline__ float wrench_linear_term(int j, int a, const float* s
 // ---------------------------------------------------------------------------------------
 // Fused condense + factor + ADMM kernel.  One CTA per problem.
 // ---------------------------------------------------------------------------------------
-template <int N, int SPLIT, int MINB>
-__global__ void __launch_bounds__(Geo<N, SPLIT>::THREADS, MINB)
+template <int N, int SPLIT, int MINB, int R>
+__global__ void __launch_bounds__((Geo<N, SPLIT, R>::THREADS), MINB)
 solve_kernel(const SolveParams p) {
-  using G_ = Geo<N, SPLIT>;
-  constexpr int NW = G_::NW, NWP = G_::NWP, COLS = G_::COLS, NLEG = G_::NLEG;
+  using G_ = Geo<N, SPLIT, R>;
+  constexpr int NW = G_::NW, NWP = G_::NWP, COLS = G_::COLS, NLEG = G_::NLEG, NWR = G_::NWR;
   constexpr int THREADS = G_::THREADS, LWARPS = G_::LWARPS, NX = G_::NX;
 
   __shared__ __align__(16) float s_x0[16];
@@ -187,6 +203,7 @@ solve_kernel(const SolveParams p) {
   const bool leg_warp = warp < LWARPS;   // warp-uniform: warps without leg threads skip leg phases
   const int slot = p.slot0 + b;
 
+  if (p.dbg_clk && blockIdx.x == 0 && tid == 0) p.dbg_clk[0] = clock64();
   // ---- phase 0: stage the per-problem record (coalesced 4-byte loads, every byte requested
   // once: the record may live in page-locked HOST memory, see cmpc_solve_host) --------------
   for (int i = tid; i < 13; i += THREADS) s_x0[i] = __ldg(p.x0 + (size_t)b * 13 + i);
@@ -212,6 +229,7 @@ solve_kernel(const SolveParams p) {
   }
   __syncthreads();
 
+  if (p.dbg_clk && blockIdx.x == 0 && tid == 0) p.dbg_clk[1] = clock64();
   float sn, cs;
   sincosf(s_x0[2], &sn, &cs);
   const float im = p.inv_mass;
@@ -244,123 +262,150 @@ solve_kernel(const SolveParams p) {
     s_G[tid][11] = stance ? 1.f : 0.f;
   }
   const bool is_row = tid < G_::ROWT;
-  const int rs = SPLIT == 1 ? 0 : tid / NW;          // slice-major layout: slice, P row
-  const int ri = tid - rs * NW;                      // (any SPLIT works, no lane alignment needed)
-  const int rj = ri / 6, ra = ri % 6;                // stage, axis of that row
-  if (is_row && rs == 0) s_h[ri] = wrench_linear_term<N>(rj, ra, s_x0, s_xd, cs, sn, p.w, p.dt);
+  const int rs = SPLIT == 1 ? 0 : tid / NWR;         // slice-major layout: column slice,
+  const int rp = tid - rs * NWR;                     // first row (rows rp + q NWR, q < R)
+  const int rj0 = rp / 6, ra = rp % 6;               // stage of the first row, axis of all R rows
+  for (int i = tid; i < NW; i += THREADS)
+    s_h[i] = wrench_linear_term<N>(i / 6, i % 6, s_x0, s_xd, cs, sn, p.w, p.dt);
   __syncthreads();
 
+  if (p.dbg_clk && blockIdx.x == 0 && tid == 0) p.dbg_clk[2] = clock64();
   // ---- phases 2+3 as a re-runnable step (adaptive rho refactorises) ------------------------
-  float row[COLS];
+  float row[R][COLS];
   auto factorize = [&]() {
   // d of this leg for the current rho (K = H + (sigma + rho) I on the stance forces)
   dinv = stance ? 1.f / (p.sigma + 2.f * p.r_weight + rho) : 0.f;
   if (is_leg) s_G[tid][9] = dinv;
   __syncthreads();
-  // ---- phase 2: P = M^-1 + E (row slices in registers) ------------------------------------
-#pragma unroll
-  for (int c = 0; c < COLS; ++c) row[c] = 0.f;
+  // ---- phase 2: P = M^-1 + E (R x COLS register tiles) -------------------------------------
   // E_j[ra][a'] = sum_l sum_c Gp[ra][c] d Gp[a'][c],  Gp = [Ghat ; I/m]
-  float E[6];
+  float E[R][6];
+  float sc[R], diag[R], rdiag[R];
+  const float* mi[R];
 #pragma unroll
-  for (int a2 = 0; a2 < 6; ++a2) E[a2] = 0.f;
-  const float* mi = p.Minv + ((size_t)(is_row ? ra : 0) * N + (is_row ? rj : 0)) * N;
-  float sc_i = 1.f;
-  if (is_row) {
+  for (int q = 0; q < R; ++q) {
+    const int rj = rj0 + q * (N / R);
+    mi[q] = p.Minv + ((size_t)(is_row ? ra : 0) * N + (is_row ? rj : 0)) * N;
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {
-      const float* g = s_G[4 * rj + l];
-      const float d = g[9];
+    for (int a2 = 0; a2 < 6; ++a2) E[q][a2] = 0.f;
+    sc[q] = 1.f; diag[q] = 1.f; rdiag[q] = 1.f;
+    if (is_row) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float mine = (ra < 3 ? g[3 * ra + c] : (ra - 3 == c ? im : 0.f)) * d;
+      for (int l = 0; l < 4; ++l) {
+        const float* g = s_G[4 * rj + l];
+        const float d = g[9];
 #pragma unroll
-        for (int a2 = 0; a2 < 3; ++a2) E[a2] += mine * g[3 * a2 + c];
-        E[3 + c] += mine * im;
+        for (int c = 0; c < 3; ++c) {
+          const float mine = (ra < 3 ? g[3 * ra + c] : (ra - 3 == c ? im : 0.f)) * d;
+#pragma unroll
+          for (int a2 = 0; a2 < 3; ++a2) E[q][a2] += mine * g[3 * a2 + c];
+          E[q][3 + c] += mine * im;
+        }
       }
+      // Jacobi scaling: the sweep runs on S P S (unit diagonal, pivots <= 1); its fused special
+      // cases lose log2(pivot) bits when pivots are >> 1
+      const float pii = __ldg(mi[q] + rj) + pick6(E[q], ra);
+      sc[q] = rsqrtf(pii);
+      diag[q] = pii * sc[q] * sc[q];
+      rdiag[q] = __fdividef(1.f, diag[q]);
+      if (rs == 0) s_S[rp + q * NWR] = sc[q];
     }
-    // Jacobi scaling: the sweep runs on S P S (unit diagonal, pivots <= 1); its fused special
-    // cases lose log2(pivot) bits when pivots are >> 1
-    sc_i = rsqrtf(__ldg(mi + rj) + E[ra]);
-    if (rs == 0) s_S[ri] = sc_i;
   }
   __syncthreads();
+#pragma unroll
+  for (int q = 0; q < R; ++q)
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) row[q][c] = 0.f;
   if (is_row) {
+    // column of tile entry c: col = rs COLS + c = 6 j2 + a2, with j2, a2 advanced from those
+    // of the slice start by compile-time steps (no runtime division per entry)
+    const int bj = (rs * COLS) / 6, ba = (rs * COLS) % 6;
 #pragma unroll
-    for (int c = 0; c < COLS; ++c) {
-      const int col = rs * COLS + c;
-      const int j2 = col / 6, a2 = col % 6;
-      float v = 0.f;
-      if (col < NW) {
-        if (a2 == ra) v = __ldg(mi + j2);
-        if (j2 == rj) {       // select instead of E[a2]: no dynamically indexed local array
-          float e = 0.f;
+    for (int q = 0; q < R; ++q) {
+      const int rj = rj0 + q * (N / R);
 #pragma unroll
-          for (int q = 0; q < 6; ++q) e = (a2 == q) ? E[q] : e;
-          v += e;
+      for (int c = 0; c < COLS; ++c) {
+        const int col = rs * COLS + c;
+        int a2 = ba + c % 6, j2 = bj + c / 6;
+        if (a2 >= 6) { a2 -= 6; ++j2; }
+        float v = 0.f;
+        if (col < NW) {
+          if (a2 == ra) v = __ldg(mi[q] + j2);
+          if (j2 == rj) v += pick6(E[q], a2);
+          v *= sc[q] * s_S[col];
         }
-        v *= sc_i * s_S[col];
+        row[q][c] = v;
       }
-      row[c] = v;
     }
   }
+  if (p.dbg_clk && blockIdx.x == 0 && tid == 0) p.dbg_clk[3] = clock64();
 
   // ---- phase 3: symmetric Gauss-Jordan sweep, rows in registers -> row = -P^-1 ------------
-  // Step k: the owner of row k publishes it through shared memory with entry k replaced by
-  // a_kk - 1, plus d = 1/a_kk.  EVERY thread then runs the same FMA stream
+  // Step k: the owners of row k (one thread per column slice) publish it through shared memory
+  // with entry k replaced by a_kk - 1, plus d = 1/a_kk.  EVERY thread then runs the same FMA
+  // stream on each of its rows
   //     row[c] += nf * p'[c],   nf = -a_ik d  (other rows),   nf = d - 1  (the pivot row itself)
   // which yields a_ic - a_ik a_kc / a_kk, a_ik / a_kk in column k, and d * p' for the pivot row.
   // Only the pivot row's own diagonal comes out as 2 - d instead of -d; the true diagonal of
   // every row is therefore tracked in a register (`diag`, also the next pivot) and the constant
   // +2 on the in-row copy is removed once at the end.  No divergent special-case path, no
-  // dynamic register indexing.
-  float diag = 1.f, rdiag = 1.f;
-  if (is_row) {
-    diag = (__ldg(mi + rj) + E[ra]) * sc_i * sc_i;
-    rdiag = __fdividef(1.f, diag);
-  }
-  for (int k = 0; k < NW; ++k) {
-    float* buf = s_row[k & 1];
-    if (is_row && ri == k) {
+  // dynamic register indexing (the pivot loop is split by the row slot q0 that holds the pivot).
 #pragma unroll
-      for (int c = 0; c < COLS; c += 4)
-        *reinterpret_cast<float4*>(buf + rs * COLS + c) =
-            make_float4(row[c], row[c + 1], row[c + 2], row[c + 3]);
-      if (k / COLS == rs) {   // this slice holds the pivot (stores of one thread stay ordered)
-        buf[k] = diag - 1.f;
-        buf[NWP] = rdiag;
+  for (int q0 = 0; q0 < R; ++q0) {
+    for (int kk = 0; kk < NWR; ++kk) {
+      const int k = q0 * NWR + kk;
+      float* buf = s_row[k & 1];
+      if (is_row && rp == kk) {
+#pragma unroll
+        for (int c = 0; c < COLS; c += 4)
+          *reinterpret_cast<float4*>(buf + rs * COLS + c) =
+              make_float4(row[q0][c], row[q0][c + 1], row[q0][c + 2], row[q0][c + 3]);
+        if (k / COLS == rs) {   // this slice holds the pivot (stores of one thread stay ordered)
+          buf[k] = diag[q0] - 1.f;
+          buf[NWP] = rdiag[q0];
+        }
       }
-    }
-    __syncthreads();
-    if (is_row) {
-      const float d = buf[NWP];
-      const float m = buf[ri];
-      const bool own = ri == k;
-      const float nf = own ? d - 1.f : -m * d;
-      diag = own ? -d : fmaf(nf, m, diag);
-      rdiag = __fdividef(1.f, diag);
-      const float* pr = buf + rs * COLS;
+      __syncthreads();
+      if (is_row) {
+        const float d = buf[NWP];
+        float nf[R];
 #pragma unroll
-      for (int c = 0; c < COLS; c += 4) {
-        const float4 pv = *reinterpret_cast<const float4*>(pr + c);
-        row[c] = fmaf(nf, pv.x, row[c]);
-        row[c + 1] = fmaf(nf, pv.y, row[c + 1]);
-        row[c + 2] = fmaf(nf, pv.z, row[c + 2]);
-        row[c + 3] = fmaf(nf, pv.w, row[c + 3]);
+        for (int q = 0; q < R; ++q) {
+          const float m = buf[rp + q * NWR];
+          const bool own = q == q0 && rp == kk;
+          nf[q] = own ? d - 1.f : -m * d;
+          diag[q] = own ? -d : fmaf(nf[q], m, diag[q]);
+          rdiag[q] = __fdividef(1.f, diag[q]);
+        }
+        const float* pr = buf + rs * COLS;
+#pragma unroll
+        for (int c = 0; c < COLS; c += 4) {
+          const float4 pv = *reinterpret_cast<const float4*>(pr + c);
+#pragma unroll
+          for (int q = 0; q < R; ++q) {
+            row[q][c] = fmaf(nf[q], pv.x, row[q][c]);
+            row[q][c + 1] = fmaf(nf[q], pv.y, row[q][c + 1]);
+            row[q][c + 2] = fmaf(nf[q], pv.z, row[q][c + 2]);
+            row[q][c + 3] = fmaf(nf[q], pv.w, row[q][c + 3]);
+          }
+        }
       }
     }
   }
   if (is_row) {   // remove the +2 of the in-row diagonal copy, undo the Jacobi scaling
 #pragma unroll
-    for (int c = 0; c < COLS; ++c) {
-      const int col = rs * COLS + c;
-      const float v = col == ri ? diag : row[c];
-      row[c] = v * sc_i * (col < NW ? s_S[col] : 0.f);
-    }
+    for (int q = 0; q < R; ++q)
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) {
+        const int col = rs * COLS + c;
+        const float v = col == rp + q * NWR ? diag[q] : row[q][c];
+        row[q][c] = v * sc[q] * (col < NW ? s_S[col] : 0.f);
+      }
   }
   __syncthreads();
   };
   factorize();
+  if (p.dbg_clk && blockIdx.x == 0 && tid == 0) p.dbg_clk[4] = clock64();
 
   // ---- phase 4: initial iterate -----------------------------------------------------------
   const float fmin = p.f_min, fmax = p.f_max;
@@ -413,12 +458,13 @@ solve_kernel(const SolveParams p) {
         *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = pick_pair(wv, ll);
     }
     __syncthreads();
-    if (is_row && rs == 0) {
-      const float* mg = p.Mg + ((size_t)ra * N + rj) * N;
+    for (int i = tid; i < NW; i += THREADS) {
+      const int a_ = i % 6;
+      const float* mg = p.Mg + (size_t)(a_ * N + i / 6) * N;
       float acc = 0.f;
 #pragma unroll
-      for (int j2 = 0; j2 < N; ++j2) acc = fmaf(__ldg(mg + j2), s_s[6 * j2 + ra], acc);
-      s_v[ri] = acc;
+      for (int j2 = 0; j2 < N; ++j2) acc = fmaf(__ldg(mg + j2), s_s[6 * j2 + a_], acc);
+      s_v[i] = acc;
     }
     __syncthreads();
     if (is_leg && stance) {
@@ -443,6 +489,7 @@ solve_kernel(const SolveParams p) {
     __syncthreads();
   }
 
+  if (p.dbg_clk && blockIdx.x == 0 && tid == 0) p.dbg_clk[5] = clock64();
   // ---- phase 5: ADMM ------------------------------------------------------------------------
   int it = 0;
   int status = 0;
@@ -539,17 +586,24 @@ solve_kernel(const SolveParams p) {
     }
     // wrench phase: q = P^-1 s   (row holds -P^-1); each slice publishes its partial sum
     if (is_row) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      float acc[R][4];
+#pragma unroll
+      for (int q = 0; q < R; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
       const float* sp = s_s + rs * COLS;
 #pragma unroll
       for (int c = 0; c < COLS; c += 4) {
         const float4 sv4 = *reinterpret_cast<const float4*>(sp + c);
-        a0 = fmaf(row[c], sv4.x, a0);
-        a1 = fmaf(row[c + 1], sv4.y, a1);
-        a2 = fmaf(row[c + 2], sv4.z, a2);
-        a3 = fmaf(row[c + 3], sv4.w, a3);
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          acc[q][0] = fmaf(row[q][c], sv4.x, acc[q][0]);
+          acc[q][1] = fmaf(row[q][c + 1], sv4.y, acc[q][1]);
+          acc[q][2] = fmaf(row[q][c + 2], sv4.z, acc[q][2]);
+          acc[q][3] = fmaf(row[q][c + 3], sv4.w, acc[q][3]);
+        }
       }
-      s_q[rs][ri] = -((a0 + a1) + (a2 + a3));
+#pragma unroll
+      for (int q = 0; q < R; ++q)
+        s_q[rs][rp + q * NWR] = -((acc[q][0] + acc[q][1]) + (acc[q][2] + acc[q][3]));
     }
     __syncthreads();
     // leg phase B: x-update, relaxed projection, dual update
@@ -581,6 +635,7 @@ solve_kernel(const SolveParams p) {
   }
   (void)rho_updates;
 
+  if (p.dbg_clk && blockIdx.x == 0 && tid == 0) p.dbg_clk[6] = clock64();
   // ---- phase 6: outputs -----------------------------------------------------------------------
   if (is_leg) {
     s_xd[3 * tid] = x[0]; s_xd[3 * tid + 1] = x[1]; s_xd[3 * tid + 2] = x[2];   // staged, stored below
@@ -655,6 +710,7 @@ solve_kernel(const SolveParams p) {
       p.X[(size_t)b * NX + o] = val;
     }
   }
+  if (p.dbg_clk && blockIdx.x == 0 && tid == 0) p.dbg_clk[7] = clock64();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -683,9 +739,7 @@ __device__ __forceinline__ int score_bucket(float s) {
 }
 
 template <int N>
-__global__ void __launch_bounds__(128) score_kernel(const ScoreParams p) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= p.B) return;
+__device__ __forceinline__ float problem_score(const ScoreParams& p, int b) {
   float sn, cs;
   sincosf(__ldg(p.x0 + (size_t)b * 13 + 2), &sn, &cs);
   float acc = 0.f;
@@ -714,7 +768,14 @@ __global__ void __launch_bounds__(128) score_kernel(const ScoreParams p) {
       cnt += 3;
     }
   }
-  const float sc = cnt ? acc / (float)cnt : 0.f;
+  return cnt ? acc / (float)cnt : 0.f;
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) score_kernel(const ScoreParams p) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.B) return;
+  const float sc = problem_score<N>(p, b);
   p.score[b] = sc;
   atomicAdd(p.hist + score_bucket(sc), 1);
 }

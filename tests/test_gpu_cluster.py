@@ -1,5 +1,6 @@
-"""Thread-block-cluster variant of the solve kernel (long horizons, N = 40 / 60, and as an
-alternative layout for N = 20 / 30): same algorithm, so the same oracle checks apply."""
+"""Alternative thread layouts of the solve kernel: the thread-block-cluster kernel (long
+horizons N = 40 / 60, optional for N = 20 / 30) and the register-blocked layouts (R rows of P
+per thread, `kernel_variant`): same algorithm, so the same oracle checks apply."""
 import numpy as np
 import pytest
 
@@ -13,7 +14,10 @@ from test_gpu_parity import gpu_solve, close, ATOL, RTOL, _FakeLite3, _Logger   
 
 
 @pytest.mark.parametrize("N,variant,gaits", [(20, 2, ("trot",)), (30, 2, GAIT_NAMES), (40, 0, ("trot",)),
-                                             (60, 0, ("pseudo_gallop",))])
+                                             (60, 0, ("pseudo_gallop",)),
+                                             # register-blocked single-CTA layouts <N,SPLIT,MINB,R>
+                                             (10, 3, GAIT_NAMES), (10, 4, GAIT_NAMES), (30, 0, ("trot",)),
+                                             (30, 1, GAIT_NAMES), (30, 3, ("trot",)), (30, 4, GAIT_NAMES)])
 def test_cluster_kernel_iterate_parity(N, variant, gaits):
     B, K = 6, (50 if N < 60 else 120)
     pb = synthetic_batch(B, N=N, gaits=gaits, seed=3)

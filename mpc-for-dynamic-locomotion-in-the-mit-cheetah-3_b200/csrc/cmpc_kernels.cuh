@@ -24,6 +24,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace cmpc {
 
@@ -186,7 +187,8 @@ solve_kernel(const SolveParams p) {
   __shared__ __align__(16) float s_xd[NX + 3];         // x_des; reused to stage U at the end
   __shared__ __align__(16) float s_r[3 * NLEG];        // lever arms as loaded (coalesced)
   __shared__ __align__(16) float s_G[NLEG][12];        // Ghat (9) + dxy, dz, pad per leg
-  __shared__ __align__(16) float s_row[2][NWP + 4];    // pivot-row double buffer (+ 1/pivot)
+  __shared__ __align__(16) float s_rowA[NWP + 4];      // pivot-row double buffer (+ 1/pivot): two
+  __shared__ __align__(16) float s_rowB[NWP + 4];      // arrays, so loads of one never alias stores to the other
   __shared__ __align__(16) float s_s[NWP];             // wrench-space rhs  s = G D^-1 b
   __shared__ __align__(16) float s_q[SPLIT][NWP];      // q = P^-1 s as SPLIT partial sums
   __shared__ __align__(16) float s_v[NWP];             // exact gradient M G x (refresh)
@@ -350,47 +352,75 @@ solve_kernel(const SolveParams p) {
   // every row is therefore tracked in a register (`diag`, also the next pivot) and the constant
   // +2 on the in-row copy is removed once at the end.  No divergent special-case path, no
   // dynamic register indexing (the pivot loop is split by the row slot q0 that holds the pivot).
+  // The owners of the NEXT pivot row store it while they update it (one predicated 16-byte
+  // store after every 4R FMAs) instead of after the update: a barrier waits for the stores in
+  // flight to drain, and 15 back-to-back stores of one lane in front of it cost more than the
+  // update itself (measured: 410 cycles per pivot on an otherwise idle SM).
+  auto publish_tail = [&](float* nbuf, int kn, float dg, float rdg) {
+    if (kn / COLS == rs) {   // this slice holds the pivot (stores of one thread stay ordered)
+      nbuf[kn] = dg - 1.f;
+      nbuf[NWP] = rdg;
+    }
+  };
+  auto sweep_step = [&](auto q0c, auto qnc, auto parc, int kk, int kn_local, bool has_next) {
+    constexpr int q0 = decltype(q0c)::value, qn = decltype(qnc)::value;
+    constexpr bool odd = decltype(parc)::value != 0;     // pivot parity picks the buffer statically
+    const float* buf = odd ? s_rowB : s_rowA;
+    float* nbuf = odd ? s_rowA : s_rowB;
+    if (is_row) {
+      const float d = buf[NWP];
+      float nf[R];
 #pragma unroll
-  for (int q0 = 0; q0 < R; ++q0) {
-    for (int kk = 0; kk < NWR; ++kk) {
-      const int k = q0 * NWR + kk;
-      float* buf = s_row[k & 1];
-      if (is_row && rp == kk) {
-#pragma unroll
-        for (int c = 0; c < COLS; c += 4)
-          *reinterpret_cast<float4*>(buf + rs * COLS + c) =
-              make_float4(row[q0][c], row[q0][c + 1], row[q0][c + 2], row[q0][c + 3]);
-        if (k / COLS == rs) {   // this slice holds the pivot (stores of one thread stay ordered)
-          buf[k] = diag[q0] - 1.f;
-          buf[NWP] = rdiag[q0];
-        }
+      for (int q = 0; q < R; ++q) {
+        const float m = buf[rp + q * NWR];
+        const bool own = q == q0 && rp == kk;
+        nf[q] = own ? d - 1.f : -m * d;
+        diag[q] = own ? -d : fmaf(nf[q], m, diag[q]);
+        rdiag[q] = __fdividef(1.f, diag[q]);
       }
-      __syncthreads();
-      if (is_row) {
-        const float d = buf[NWP];
-        float nf[R];
+      const bool pub = has_next && rp == kn_local;
+      const float* pr = buf + rs * COLS;
+#pragma unroll
+      for (int c = 0; c < COLS; c += 4) {
+        const float4 pv = *reinterpret_cast<const float4*>(pr + c);
 #pragma unroll
         for (int q = 0; q < R; ++q) {
-          const float m = buf[rp + q * NWR];
-          const bool own = q == q0 && rp == kk;
-          nf[q] = own ? d - 1.f : -m * d;
-          diag[q] = own ? -d : fmaf(nf[q], m, diag[q]);
-          rdiag[q] = __fdividef(1.f, diag[q]);
+          row[q][c] = fmaf(nf[q], pv.x, row[q][c]);
+          row[q][c + 1] = fmaf(nf[q], pv.y, row[q][c + 1]);
+          row[q][c + 2] = fmaf(nf[q], pv.z, row[q][c + 2]);
+          row[q][c + 3] = fmaf(nf[q], pv.w, row[q][c + 3]);
         }
-        const float* pr = buf + rs * COLS;
-#pragma unroll
-        for (int c = 0; c < COLS; c += 4) {
-          const float4 pv = *reinterpret_cast<const float4*>(pr + c);
-#pragma unroll
-          for (int q = 0; q < R; ++q) {
-            row[q][c] = fmaf(nf[q], pv.x, row[q][c]);
-            row[q][c + 1] = fmaf(nf[q], pv.y, row[q][c + 1]);
-            row[q][c + 2] = fmaf(nf[q], pv.z, row[q][c + 2]);
-            row[q][c + 3] = fmaf(nf[q], pv.w, row[q][c + 3]);
-          }
-        }
+        if (pub)
+          *reinterpret_cast<float4*>(nbuf + rs * COLS + c) =
+              make_float4(row[qn][c], row[qn][c + 1], row[qn][c + 2], row[qn][c + 3]);
       }
+      if (pub) publish_tail(nbuf, qn * NWR + kn_local, diag[qn], rdiag[qn]);
     }
+    __syncthreads();
+  };
+  if (is_row && rp == 0) {   // pivot 0
+#pragma unroll
+    for (int c = 0; c < COLS; c += 4)
+      *reinterpret_cast<float4*>(s_rowA + rs * COLS + c) = make_float4(row[0][c], row[0][c + 1], row[0][c + 2], row[0][c + 3]);
+    publish_tail(s_rowA, 0, diag[0], rdiag[0]);
+  }
+  __syncthreads();
+  {
+    static_assert(NWR % 2 == 0, "pivots are processed in (even, odd) pairs");
+    using I0 = std::integral_constant<int, 0>;
+    using I1 = std::integral_constant<int, 1>;
+    auto blocks = [&](auto self, auto q0c) -> void {
+      constexpr int q0 = decltype(q0c)::value;
+      constexpr int qn = q0 + 1 < R ? q0 + 1 : q0;
+      for (int kk = 0; kk + 2 < NWR; kk += 2) {
+        sweep_step(q0c, q0c, I0{}, kk, kk + 1, true);
+        sweep_step(q0c, q0c, I1{}, kk + 1, kk + 2, true);
+      }
+      sweep_step(q0c, q0c, I0{}, NWR - 2, NWR - 1, true);
+      sweep_step(q0c, std::integral_constant<int, qn>{}, I1{}, NWR - 1, 0, q0 + 1 < R);
+      if constexpr (q0 + 1 < R) self(self, std::integral_constant<int, q0 + 1>{});
+    };
+    blocks(blocks, I0{});
   }
   if (is_row) {   // remove the +2 of the in-row diagonal copy, undo the Jacobi scaling
 #pragma unroll

@@ -167,6 +167,22 @@ int cmpc_plant_step(cmpc_handle* h, int32_t B, const cmpc_gait_tables* gt, int32
                     float* x, const float* r, const float* U, const float* x_des,
                     float* yaw_start, float* com_start, float* track_err, void* stream);
 
+/* Leg controllers that consume the solve (src/main.py:193-282) for B
+ * robots at the tick stored in `tick`: stance legs get tau = J'(-f) with f = U[:,0,leg]
+ * (ground_controller, src/main.py:203-214), swing legs the PD + feed-forward law of
+ * swing_leg_controller (src/main.py:219-282) on the swing reference of
+ * src/foot_trajectory_generator.py:27-96.  Which legs are stance follows src/main.py:152-160.
+ * DEVICE pointers: U [B,N,12]; J, Jdot, Mleg [B,4,3,3] (the leg's 3x3 blocks of DART's
+ * getLinearJacobian / getJacobianClassicDeriv[3:] / getMassMatrix()[3:6]); cg, dq, foot_pos,
+ * foot_vel [B,4,3]; outputs tau [B,4,3], p_des [B,4,3] (nullable, the desired foot position
+ * the reference logs), stance [B] uint8 bits (nullable).  kp, kd: HOST pointers to the 3
+ * diagonal gains (reference: 250, 15). */
+int cmpc_leg_torques(cmpc_handle* h, int32_t B, const cmpc_gait_tables* gt, const int32_t* tick,
+                     const float* U, const float* J, const float* Jdot, const float* Mleg,
+                     const float* cg, const float* dq, const float* foot_pos, const float* foot_vel,
+                     const float* kp, const float* kd, float* tau, float* p_des, uint8_t* stance,
+                     void* stream);
+
 /* Measures the FP32 FMA throughput of `device` (TFLOP/s, best of 4 timed launches of an 8-chain
  * FMA kernel): the denominator of the on-chip roofline of the solve kernel. */
 int cmpc_fp32_peak(int32_t device, float* tflops);

@@ -13,3 +13,4 @@ __version__ = "0.1.0"
 from . import sharding                                           # noqa: F401,E402
 from .rollout import ClosedLoopRollout                           # noqa: F401,E402
 from . import logexport                                          # noqa: F401,E402
+from .controllers import BatchedLegController                    # noqa: F401,E402

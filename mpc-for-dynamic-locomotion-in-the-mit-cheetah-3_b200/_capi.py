@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 SYMBOLS = ("cmpc_default_config", "cmpc_create", "cmpc_destroy", "cmpc_solve", "cmpc_solve_host",
            "cmpc_condense", "cmpc_reset_warm", "cmpc_get_warm", "cmpc_set_warm",
            "cmpc_launch_count", "cmpc_supported_horizons", "cmpc_version", "cmpc_last_error",
-           "cmpc_assemble", "cmpc_plant_step", "cmpc_fp32_peak")
+           "cmpc_assemble", "cmpc_plant_step", "cmpc_fp32_peak", "cmpc_leg_torques")
 
 
 class CmpcError(RuntimeError):
@@ -104,6 +104,7 @@ def lib() -> C.CDLL:
     gtp = C.POINTER(GaitTables)
     L.cmpc_assemble.argtypes = [vp, i32, gtp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.cmpc_plant_step.argtypes = [vp, i32, gtp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.cmpc_leg_torques.argtypes = [vp, i32, gtp] + [vp] * 9 + [C.POINTER(C.c_float)] * 2 + [vp] * 4
     L.cmpc_fp32_peak.argtypes = [i32, C.POINTER(C.c_float)]
     L.cmpc_launch_count.argtypes = [vp]
     L.cmpc_launch_count.restype = C.c_int64

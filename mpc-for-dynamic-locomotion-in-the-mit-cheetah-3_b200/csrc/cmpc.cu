@@ -505,6 +505,31 @@ int cmpc_plant_step(cmpc_handle* h, int32_t B, const cmpc_gait_tables* gt, int32
   return CMPC_OK;
 }
 
+int cmpc_leg_torques(cmpc_handle* h, int32_t B, const cmpc_gait_tables* gt, const int32_t* tick,
+                     const float* U, const float* J, const float* Jdot, const float* Mleg,
+                     const float* cg, const float* dq, const float* foot_pos, const float* foot_vel,
+                     const float* kp, const float* kd, float* tau, float* p_des, uint8_t* stance,
+                     void* stream) {
+  if (!h) return fail(CMPC_ERR_INVALID, "null handle");
+  if (B < 0) return fail(CMPC_ERR_INVALID, "negative batch");
+  int rc = check_gait(gt);
+  if (rc) return rc;
+  if (B == 0) return CMPC_OK;
+  if (!tick || !U || !J || !Jdot || !Mleg || !cg || !dq || !foot_pos || !foot_vel || !kp || !kd || !tau)
+    return fail(CMPC_ERR_INVALID, "null pointer");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  cmpc::LegParams p{};
+  fill_gait(h, gt, p.gt);
+  p.tick = tick; p.U = U; p.J = J; p.Jdot = Jdot; p.Mleg = Mleg; p.cg = cg; p.dq = dq;
+  p.foot_pos = foot_pos; p.foot_vel = foot_vel; p.tau = tau; p.p_des = p_des; p.stance = stance;
+  p.B = B; p.N = h->cfg.N;
+  for (int i = 0; i < 3; ++i) { p.kp[i] = kp[i]; p.kd[i] = kd[i]; }
+  cmpc::leg_torque_kernel<<<(4 * B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  h->launches.fetch_add(1);
+  return CMPC_OK;
+}
+
 int cmpc_fp32_peak(int32_t device, float* tflops) {
   if (!tflops) return fail(CMPC_ERR_INVALID, "null pointer");
   int ndev = 0;

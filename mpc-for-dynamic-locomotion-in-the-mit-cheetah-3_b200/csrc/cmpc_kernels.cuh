@@ -1067,6 +1067,110 @@ __global__ void __launch_bounds__(128) plant_kernel(const PlantParams p) {
 
 __global__ void tick_kernel(int32_t* tick) { *tick += 1; }
 
+// ---------------------------------------------------------------------------------------
+// Leg controllers on the output side of the MPC: one thread per
+// (robot, leg) turns the first-stage force of the solve, the simulator's leg Jacobians /
+// inertia / bias forces and the gait tables into joint torques.
+//   stance leg:  tau = J' (-f)                                      (reference src/main.py:203-214)
+//   swing  leg:  tau = J' (Kp (p_des - p) + Kd (v_des - v))
+//                    + J' (J*M*J') (a_des - Jdot dq) + CG          (src/main.py:219-282; J*M*J' is the
+//                                                                   ELEMENTWISE product, as in the reference)
+// with the swing reference p_des, v_des, a_des of src/foot_trajectory_generator.py:27-96 (cubic
+// xy, quartic z over 0.8 ss, z clamp of src/main.py:229-231) and the controller's stance mask
+// (planned feet_id while time_in_step <= ss, all-stance afterwards - src/main.py:152-160 with the
+// side effect of foot_trajectory_generator.py:53-54).  Streaming, HBM-bound: 57 floats in,
+// 6 floats + 1 byte out per leg.
+// ---------------------------------------------------------------------------------------
+struct LegParams {
+  GaitTables gt;
+  const int32_t* __restrict__ tick;      // [1] current tick (device)
+  const float* __restrict__ U;           // [B,N,12] forces of the solve (stage 0 is applied)
+  const float* __restrict__ J;           // [B,4,3,3] linear foot Jacobian, leg columns, world frame
+  const float* __restrict__ Jdot;        // [B,4,3,3]
+  const float* __restrict__ Mleg;        // [B,4,3,3] rows 3:6 of the mass matrix, leg columns
+  const float* __restrict__ cg;          // [B,4,3] Coriolis + gravity of the leg joints
+  const float* __restrict__ dq;          // [B,4,3] joint velocities
+  const float* __restrict__ foot_pos;    // [B,4,3] measured
+  const float* __restrict__ foot_vel;    // [B,4,3]
+  float* __restrict__ tau;               // [B,4,3]
+  float* __restrict__ p_des;             // [B,4,3] desired foot position (what the reference logs), nullable
+  uint8_t* __restrict__ stance;          // [B] stance bits the controller used, nullable
+  int32_t B, N;
+  float kp[3], kd[3];
+};
+
+__global__ void __launch_bounds__(128) leg_torque_kernel(const LegParams p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.B * 4) return;
+  const int b = idx >> 2, l = idx & 3;
+  const GaitTables& gt = p.gt;
+  const int t = *p.tick;
+  const int ss = gt.ss[b], period = ss + gt.ds[b];
+  int step = t / period;
+  if (step > gt.S - 1) step = gt.S - 1;
+  const int tin = t - step * period;
+  const int bits = tin <= ss ? (int)gt.feet_id[(size_t)b * gt.S + step] : 0xF;
+  const bool is_stance = (bits >> l) & 1;
+  const int nxt = step + 1 < gt.S ? step + 1 : step;
+  const float* p0 = gt.plan_pos + (((size_t)b * gt.S + step) * 4 + l) * 3;
+  const float* p1 = gt.plan_pos + (((size_t)b * gt.S + nxt) * 4 + l) * 3;
+  float pd[3] = {p0[0], p0[1], p0[2]}, vd[3] = {0.f, 0.f, 0.f}, ad[3] = {0.f, 0.f, 0.f};
+  if (!is_stance && step != 0) {
+    const float ts = 0.8f * (float)ss, tt = (float)tin;
+    if (tt >= ts) {
+      pd[0] = p1[0]; pd[1] = p1[1]; pd[2] = p1[2];
+    } else {
+      const float u = tt / ts, idt = 1.f / gt.dt;
+      const float s0 = u * u * (3.f - 2.f * u);                      // -2u^3 + 3u^2
+      const float s1 = 6.f * u * (1.f - u) / ts * idt;               // d/dt, per second
+      const float s2 = 6.f * (1.f - 2.f * u) / (ts * ts) * idt * idt;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float d = p1[k] - p0[k];
+        pd[k] = p0[k] + d * s0; vd[k] = d * s1; ad[k] = d * s2;
+      }
+      const float h16 = 16.f * gt.step_height;
+      const float um = u - 1.f;
+      pd[2] = p0[2] + h16 * u * u * um * um;                         // 16h (u^4 - 2u^3 + u^2)
+      vd[2] = h16 * (4.f * u * u * u - 6.f * u * u + 2.f * u) / ts * idt;
+      ad[2] = h16 * (12.f * u * u - 12.f * u + 2.f) / (ts * ts) * idt * idt;
+      if (pd[2] < 0.f) { pd[2] = 0.f; vd[2] = 0.f; }
+    }
+  }
+  const size_t o3 = (size_t)idx * 3, o9 = (size_t)idx * 9;
+  float Jl[3][3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Jl[i / 3][i % 3] = __ldg(p.J + o9 + i);
+  float w[3];                                                        // task-space vector, tau = J' w (+ CG)
+  float bias[3] = {0.f, 0.f, 0.f};
+  if (is_stance) {
+    const float* f = p.U + (size_t)b * p.N * 12 + 3 * l;
+    w[0] = -__ldg(f); w[1] = -__ldg(f + 1); w[2] = -__ldg(f + 2);
+  } else {
+    float e[3];                                                      // a_des - Jdot dq
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float acc = ad[i];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) acc -= __ldg(p.Jdot + o9 + 3 * i + k) * __ldg(p.dq + o3 + k);
+      e[i] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float acc = p.kp[i] * (pd[i] - __ldg(p.foot_pos + o3 + i)) + p.kd[i] * (vd[i] - __ldg(p.foot_vel + o3 + i));
+#pragma unroll
+      for (int k = 0; k < 3; ++k) acc += Jl[i][k] * __ldg(p.Mleg + o9 + 3 * i + k) * Jl[k][i] * e[k];
+      w[i] = acc;
+      bias[i] = __ldg(p.cg + o3 + i);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    p.tau[o3 + k] = Jl[0][k] * w[0] + Jl[1][k] * w[1] + Jl[2][k] * w[2] + bias[k];
+  if (p.p_des) { p.p_des[o3] = pd[0]; p.p_des[o3 + 1] = pd[1]; p.p_des[o3 + 2] = pd[2]; }
+  if (p.stance && l == 0) p.stance[b] = (uint8_t)bits;
+}
+
 // FP32 FMA micro-benchmark: the denominator of the on-chip roofline.
 // 8 independent FMA chains per thread, 256 threads, grid = a multiple of the SM count.
 __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b) {

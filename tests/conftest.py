@@ -24,3 +24,8 @@ def gold():
 @pytest.fixture(scope="session")
 def gait_gold():
     return np.load(os.path.join(GOLDEN, "gait_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def swing_gold():
+    return np.load(os.path.join(GOLDEN, "swing_golden.npz"))

@@ -89,6 +89,8 @@ typedef struct cmpc_config {
                            reads the inputs and writes the results directly in host memory over
                            PCIe (no staging copies, transfers overlap the solve CTA by CTA);
                            0 = chunked cudaMemcpyAsync pipeline                              */
+  int32_t time_kernel;  /* 1 = bracket every solve-kernel launch of cmpc_solve with CUDA events on the
+                           launching stream (read back with cmpc_last_kernel_ms); 0 = off (default) */
 } cmpc_config;
 
 typedef struct cmpc_handle cmpc_handle;
@@ -186,6 +188,11 @@ int cmpc_leg_torques(cmpc_handle* h, int32_t B, const cmpc_gait_tables* gt, cons
 /* Measures the FP32 FMA throughput of `device` (TFLOP/s, best of 4 timed launches of an 8-chain
  * FMA kernel): the denominator of the on-chip roofline of the solve kernel. */
 int cmpc_fp32_peak(int32_t device, float* tflops);
+
+/* Duration in ms of the solve kernel of the most recent cmpc_solve (cfg.time_kernel = 1):
+ * CUDA events recorded on the launching stream immediately around that one kernel, i.e. without
+ * the two scheduling kernels in front of it.  Synchronises on the closing event. */
+int cmpc_last_kernel_ms(cmpc_handle* h, float* ms);
 
 /* Number of kernels this library has launched on behalf of `h` since creation. */
 int64_t cmpc_launch_count(const cmpc_handle* h);

@@ -77,6 +77,8 @@ struct cmpc_handle {
   int32_t* d_order = nullptr;
   int32_t* d_hist = nullptr;
   Staging st;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // cfg.time_kernel
+  bool timed = false;
   std::atomic<int64_t> launches{0};
 };
 
@@ -384,11 +386,21 @@ int cmpc_destroy(cmpc_handle* h) {
   cudaFree(h->st.d_out);
   for (auto& s : h->st.streams)
     if (s) cudaStreamDestroy(s);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
   return CMPC_OK;
 }
 
 int64_t cmpc_launch_count(const cmpc_handle* h) { return h ? h->launches.load() : 0; }
+
+int cmpc_last_kernel_ms(cmpc_handle* h, float* ms) {
+  if (!h || !ms) return fail(CMPC_ERR_INVALID, "null argument");
+  if (!h->timed) return fail(CMPC_ERR_INVALID, "no timed solve yet (set cfg.time_kernel and call cmpc_solve)");
+  CUDA_TRY(cudaEventSynchronize(h->ev1));
+  CUDA_TRY(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return CMPC_OK;
+}
 
 int cmpc_solve(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, const float* r,
                const uint8_t* mask, const float* x_des, const float* mu, float* U, float* X,
@@ -408,7 +420,15 @@ int cmpc_solve(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, const 
   if (rc) return rc;
   static const bool dbg = std::getenv("CMPC_DEBUG_CLOCKS") != nullptr;   // developer aid, synchronous
   if (dbg) CUDA_TRY(cudaMalloc(&p.dbg_clk, 8 * sizeof(long long)));
+  if (h->cfg.time_kernel) {
+    if (!h->ev0) { CUDA_TRY(cudaEventCreate(&h->ev0)); CUDA_TRY(cudaEventCreate(&h->ev1)); }
+    CUDA_TRY(cudaEventRecord(h->ev0, (cudaStream_t)stream));
+  }
   CUDA_TRY(pick_solve(h->cfg)(p, (cudaStream_t)stream));
+  if (h->cfg.time_kernel) {
+    CUDA_TRY(cudaEventRecord(h->ev1, (cudaStream_t)stream));
+    h->timed = true;
+  }
   h->launches.fetch_add(1);
   if (dbg) {
     long long c[8];

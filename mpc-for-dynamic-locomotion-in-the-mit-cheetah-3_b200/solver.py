@@ -174,6 +174,13 @@ class BatchedMPC:
                                               C.c_void_p(s)))
 
     @property
+    def last_kernel_ms(self) -> float:
+        """Duration of the solve kernel of the last :meth:`solve` (needs ``time_kernel=1``)."""
+        v = C.c_float()
+        _capi.check(_capi.lib().cmpc_last_kernel_ms(self._h, C.byref(v)))
+        return float(v.value)
+
+    @property
     def launch_count(self) -> int:
         return int(_capi.lib().cmpc_launch_count(self._h))
 

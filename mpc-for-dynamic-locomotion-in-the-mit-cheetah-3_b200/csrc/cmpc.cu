@@ -200,6 +200,7 @@ void fill_solve_params(const cmpc_handle* h, cmpc::SolveParams& p) {
 int schedule_batch(cmpc_handle* h, cmpc::SolveParams& p, int order_off, int hist_slot, cudaStream_t s) {
   p.order = nullptr;
   if (!h->cfg.lpt_schedule || p.B < h->cfg.lpt_schedule) return CMPC_OK;
+  if ((reinterpret_cast<uintptr_t>(p.r) & 15u) != 0) return CMPC_OK;   // score_kernel reads r with 16-byte loads
   const cmpc_config& c = h->cfg;
   cmpc::ScoreParams sp{};
   sp.x0 = p.x0; sp.r = p.r; sp.mask = p.mask; sp.Mg = h->d_Mg;

@@ -133,41 +133,41 @@ __device__ __forceinline__ void leg_map(float c, float s, const float ib[3], flo
   }
 }
 
+// Tracking error of the free response at stage k on wrench axis a (position-like and
+// velocity-like part; angular velocity error rotated by Rz):  e = free response - x_des.
+__device__ __forceinline__ void stage_error(int k, int a, const float* sx0, const float* sxd, float c,
+                                            float s, float dt, float& e_pos, float& e_vel) {
+  const float* xd = sxd + 13 * k;
+  const float kf = (float)k;
+  if (a < 3) {
+    const float rw0 = a == 0 ? (c * sx0[6] - s * sx0[7]) : (a == 1 ? (s * sx0[6] + c * sx0[7]) : sx0[8]);
+    const float rwd = a == 0 ? (c * xd[6] - s * xd[7]) : (a == 1 ? (s * xd[6] + c * xd[7]) : xd[8]);
+    e_pos = (sx0[a] - xd[a]) + kf * dt * rw0;      // exact difference first
+    e_vel = rw0 - rwd;
+  } else {
+    const int aa = a - 3;
+    float pf = (sx0[3 + aa] - xd[3 + aa]) + kf * dt * sx0[9 + aa];
+    float vf = sx0[9 + aa] - xd[9 + aa];
+    if (aa == 2) {
+      const float g = sx0[12];
+      pf += 0.5f * kf * (kf - 1.f) * dt * dt * g;
+      vf += kf * dt * g;
+    }
+    e_pos = pf;
+    e_vel = vf;
+  }
+}
+
 // Linear term of the wrench-space cost: h[6j+a] = 2 sum_{k>j} (w_pos d^2 (k-1-j) e_pos + w_vel d e_vel)
-// with e = free response - x_des (angular velocity error rotated by Rz).
 template <int N>
 __device__ __forceinline__ float wrench_linear_term(int j, int a, const float* sx0,
                                                     const float* sxd, float c, float s,
                                                     const float* w, float dt) {
-  const float g = sx0[12];
-  const float rw0x = c * sx0[6] - s * sx0[7];
-  const float rw0y = s * sx0[6] + c * sx0[7];
-  const float rw0z = sx0[8];
+  const float wp = w[a], wv = w[6 + a];      // w[0:3] Theta, w[3:6] p, w[6:9] omega, w[9:12] v
   float acc = 0.f;
   for (int k = j + 1; k <= N; ++k) {
-    const float* xd = sxd + 13 * k;
-    const float kf = (float)k;
-    float e_pos, e_vel, wp, wv;
-    if (a < 3) {
-      const float rw0 = a == 0 ? rw0x : (a == 1 ? rw0y : rw0z);
-      const float rwd = a == 0 ? (c * xd[6] - s * xd[7]) : (a == 1 ? (s * xd[6] + c * xd[7]) : xd[8]);
-      e_pos = (sx0[a] - xd[a]) + kf * dt * rw0;      // exact difference first
-      e_vel = rw0 - rwd;
-      wp = w[a];
-      wv = w[6 + a];
-    } else {
-      const int aa = a - 3;
-      float pf = (sx0[3 + aa] - xd[3 + aa]) + kf * dt * sx0[9 + aa];
-      float vf = sx0[9 + aa] - xd[9 + aa];
-      if (aa == 2) {
-        pf += 0.5f * kf * (kf - 1.f) * dt * dt * g;
-        vf += kf * dt * g;
-      }
-      e_pos = pf;
-      e_vel = vf;
-      wp = w[3 + aa];
-      wv = w[9 + aa];
-    }
+    float e_pos, e_vel;
+    stage_error(k, a, sx0, sxd, c, s, dt, e_pos, e_vel);
     acc += 2.f * (wp * dt * dt * (float)(k - 1 - j) * e_pos + wv * dt * e_vel);
   }
   return acc;
@@ -267,8 +267,23 @@ solve_kernel(const SolveParams p) {
   const int rs = SPLIT == 1 ? 0 : tid / NWR;         // slice-major layout: column slice,
   const int rp = tid - rs * NWR;                     // first row (rows rp + q NWR, q < R)
   const int rj0 = rp / 6, ra = rp % 6;               // stage of the first row, axis of all R rows
-  for (int i = tid; i < NW; i += THREADS)
-    s_h[i] = wrench_linear_term<N>(i / 6, i % 6, s_x0, s_xd, cs, sn, p.w, p.dt);
+  {
+    // linear term h in two steps: the 6N stage errors once (one (k, a) per thread), then the
+    // suffix sums over k > j - the same terms in the same order as wrench_linear_term()
+    float* e_pos = &s_pre[0][0];          // [N][6], free until the output phase
+    float* e_vel = &s_pre[1][0];
+    for (int i = tid; i < NW; i += THREADS)
+      stage_error(i / 6 + 1, i % 6, s_x0, s_xd, cs, sn, p.dt, e_pos[i], e_vel[i]);
+    __syncthreads();
+    for (int i = tid; i < NW; i += THREADS) {
+      const int j = i / 6, a = i % 6;
+      const float wp = p.w[a], wv = p.w[6 + a], dt = p.dt;
+      float acc = 0.f;
+      for (int k = j + 1; k <= N; ++k)
+        acc += 2.f * (wp * dt * dt * (float)(k - 1 - j) * e_pos[6 * (k - 1) + a] + wv * dt * e_vel[6 * (k - 1) + a]);
+      s_h[i] = acc;
+    }
+  }
   __syncthreads();
 
   if (p.dbg_clk && blockIdx.x == 0 && tid == 0) p.dbg_clk[2] = clock64();
@@ -698,6 +713,7 @@ solve_kernel(const SolveParams p) {
     }
     __syncthreads();
     // prefix sums of the wrench sequence per axis: c1[k] = sum_{j<k} w_j, c2[k] = sum_{j<k} (k-1-j) w_j
+    // (6 threads, serial in k: measured faster than one (axis, k) pair per thread)
     float* c1 = &s_pre[0][0];            // [6][N+1]
     float* c2 = &s_pre[1][0];
     if (tid < 6) {

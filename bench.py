@@ -26,8 +26,8 @@ import numpy as np  # noqa: E402
 
 BATCH = 4096
 HORIZON = 10
-KERNEL_NAMES = {10: "cmpc::solve_kernel<10,1,8,1>", 20: "cmpc::solve_kernel<20,2,2,1>",
-                30: "cmpc::solve_kernel<30,6,1,3>", 40: "cmpc::solve_cluster_kernel<10,4,4,1>",
+KERNEL_NAMES = {10: "cmpc::solve_kernel<10,1,8,1,false>", 20: "cmpc::solve_kernel<20,2,2,1,false>",
+                30: "cmpc::solve_kernel<30,6,1,3,false>", 40: "cmpc::solve_cluster_kernel<10,4,4,1>",
                 60: "cmpc::solve_cluster_kernel<10,6,6,1>"}
 WORKLOAD = "config2: batch 4096 Lite3 trot MPC QPs per GPU, N=10, randomized CoM states/velocity refs, cold start"
 

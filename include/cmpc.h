@@ -89,6 +89,16 @@ typedef struct cmpc_config {
                            reads the inputs and writes the results directly in host memory over
                            PCIe (no staging copies, transfers overlap the solve CTA by CTA);
                            0 = chunked cudaMemcpyAsync pipeline                              */
+  int32_t cache_factorization; /* 1 = keep every slot's factorisation on the device and reuse it in the
+                           next cmpc_solve of that slot while its lever arms (to cache_tol_r), yaw
+                           (cache_tol_yaw), contact masks and rho are unchanged - standing robots,
+                           static contact schedules (closed-loop use); 0 = refactorise every call.
+                           (One entry per gait phase was tried for steady-state walking: the lever
+                           arms of successive gait cycles differ by more than a safe tolerance.)
+                           Costs 4*6N*(6N+20) bytes per slot.  Compiled for N = 10 and N = 30 (default
+                           thread layout; kernel_variant is ignored), other horizons: UNSUPPORTED. */
+  float cache_tol_r, cache_tol_yaw; /* metres / radians (defaults 2e-3, 2e-3)               */
+  int32_t cache_max_iter;  /* a solve that needs more iterations drops its cache entry (30) */
   int32_t time_kernel;  /* 1 = bracket every solve-kernel launch of cmpc_solve with CUDA events on the
                            launching stream (read back with cmpc_last_kernel_ms); 0 = off (default) */
 } cmpc_config;
@@ -188,6 +198,17 @@ int cmpc_leg_torques(cmpc_handle* h, int32_t B, const cmpc_gait_tables* gt, cons
 /* Measures the FP32 FMA throughput of `device` (TFLOP/s, best of 4 timed launches of an 8-chain
  * FMA kernel): the denominator of the on-chip roofline of the solve kernel. */
 int cmpc_fp32_peak(int32_t device, float* tflops);
+
+/* Running totals of a rollout, one launch: acc[0] += sum(iters), acc[1] += #(status != solved),
+ * acc[2] += factorisation-cache hits of slots [slot0, slot0+B) in the last solve (0 without the
+ * cache).  iters, status [B] and acc [3] (64-bit unsigned) are DEVICE pointers. */
+int cmpc_accumulate_stats(cmpc_handle* h, int32_t B, int32_t slot0, const int32_t* iters,
+                          const int32_t* status, uint64_t* acc, void* stream);
+
+/* Factorisation-cache bookkeeping of slots [slot0, slot0+B) (cfg.cache_factorization): copies
+ * meta [B,4] = {rho of the cached factor, yaw it was computed at, valid (0/1), reused by the
+ * last cmpc_solve (0/1)} to a DEVICE buffer. */
+int cmpc_get_cache_meta(cmpc_handle* h, int32_t B, int32_t slot0, float* meta, void* stream);
 
 /* Duration in ms of the solve kernel of the most recent cmpc_solve (cfg.time_kernel = 1):
  * CUDA events recorded on the launching stream immediately around that one kernel, i.e. without

@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 SYMBOLS = ("cmpc_default_config", "cmpc_create", "cmpc_destroy", "cmpc_solve", "cmpc_solve_host",
            "cmpc_condense", "cmpc_reset_warm", "cmpc_get_warm", "cmpc_set_warm",
            "cmpc_launch_count", "cmpc_supported_horizons", "cmpc_version", "cmpc_last_error",
-           "cmpc_assemble", "cmpc_plant_step", "cmpc_fp32_peak", "cmpc_leg_torques", "cmpc_last_kernel_ms")
+           "cmpc_assemble", "cmpc_plant_step", "cmpc_fp32_peak", "cmpc_leg_torques", "cmpc_last_kernel_ms", "cmpc_get_cache_meta", "cmpc_accumulate_stats")
 
 
 class CmpcError(RuntimeError):
@@ -45,7 +45,9 @@ class Config(C.Structure):
                 ("adaptive_rho_interval", C.c_int32), ("adaptive_rho_tolerance", C.c_float),
                 ("rho_min", C.c_float), ("rho_max", C.c_float),
                 ("kernel_variant", C.c_int32), ("lpt_schedule", C.c_int32),
-                ("device", C.c_int32), ("host_zero_copy", C.c_int32), ("time_kernel", C.c_int32)]
+                ("device", C.c_int32), ("host_zero_copy", C.c_int32), ("cache_factorization", C.c_int32),
+                ("cache_tol_r", C.c_float), ("cache_tol_yaw", C.c_float), ("cache_max_iter", C.c_int32),
+                ("time_kernel", C.c_int32)]
 
 
 class GaitTables(C.Structure):
@@ -107,6 +109,8 @@ def lib() -> C.CDLL:
     L.cmpc_leg_torques.argtypes = [vp, i32, gtp] + [vp] * 9 + [C.POINTER(C.c_float)] * 2 + [vp] * 4
     L.cmpc_fp32_peak.argtypes = [i32, C.POINTER(C.c_float)]
     L.cmpc_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.cmpc_get_cache_meta.argtypes = [vp, i32, i32, vp, vp]
+    L.cmpc_accumulate_stats.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     L.cmpc_launch_count.argtypes = [vp]
     L.cmpc_launch_count.restype = C.c_int64
     L.cmpc_supported_horizons.argtypes = [C.POINTER(C.c_int32), i32]

@@ -76,6 +76,11 @@ struct cmpc_handle {
   float* d_score = nullptr;      // LPT scheduling scratch
   int32_t* d_order = nullptr;
   int32_t* d_hist = nullptr;
+  float4* d_cache_pinv = nullptr;   // cfg.cache_factorization
+  float* d_cache_r = nullptr;
+  uint8_t* d_cache_mask = nullptr;
+  float* d_cache_meta = nullptr;
+  uint8_t* d_cache_hit = nullptr;
   Staging st;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // cfg.time_kernel
   bool timed = false;
@@ -89,9 +94,9 @@ using CondenseLaunch = cudaError_t (*)(const cmpc::CondenseParams&, cudaStream_t
 using ScoreLaunch = cudaError_t (*)(const cmpc::ScoreParams&, cudaStream_t);
 using AssembleLaunch = cudaError_t (*)(const cmpc::AssembleParams&, cudaStream_t);
 
-template <int N, int SPLIT, int MINB, int R = 1>
+template <int N, int SPLIT, int MINB, int R = 1, bool CACHE = false>
 cudaError_t launch_solve(const cmpc::SolveParams& p, cudaStream_t s) {
-  cmpc::solve_kernel<N, SPLIT, MINB, R><<<p.B, cmpc::Geo<N, SPLIT, R>::THREADS, 0, s>>>(p);
+  cmpc::solve_kernel<N, SPLIT, MINB, R, CACHE><<<p.B, cmpc::Geo<N, SPLIT, R>::THREADS, 0, s>>>(p);
   return cudaGetLastError();
 }
 // one thread-block cluster of CL CTAs per problem (long horizons, see cmpc_cluster.cuh)
@@ -134,6 +139,7 @@ struct HorizonEntry {
   CondenseLaunch condense;
   ScoreLaunch score;
   AssembleLaunch assemble;
+  SolveLaunch solve_cached;  // default layout with the factorisation cache compiled in, or nullptr
 };
 
 // Horizons with compiled kernels.  <N, SPLIT, MINB, R>: a thread owns an R x (6N/SPLIT) register
@@ -145,11 +151,11 @@ const HorizonEntry kHorizons[] = {
     {4, {launch_solve<4, 1, 8>, nullptr, nullptr}, launch_condense<4>, launch_score<4>, launch_assemble<4>},
     {5, {launch_solve<5, 1, 8>, nullptr, nullptr}, launch_condense<5>, launch_score<5>, launch_assemble<5>},
     {8, {launch_solve<8, 1, 8>, nullptr, nullptr}, launch_condense<8>, launch_score<8>, launch_assemble<8>},
-    {10, {launch_solve<10, 1, 8>, launch_solve<10, 2, 4>, launch_solve<10, 4, 2>, launch_solve<10, 2, 8, 2>, launch_solve<10, 5, 8, 5>}, launch_condense<10>, launch_score<10>, launch_assemble<10>},
+    {10, {launch_solve<10, 1, 8>, launch_solve<10, 2, 4>, launch_solve<10, 4, 2>, launch_solve<10, 2, 8, 2>, launch_solve<10, 5, 8, 5>}, launch_condense<10>, launch_score<10>, launch_assemble<10>, launch_solve<10, 1, 8, 1, true>},
     {12, {launch_solve<12, 2, 4>, nullptr, nullptr}, launch_condense<12>, launch_score<12>, launch_assemble<12>},
     {16, {launch_solve<16, 2, 3>, nullptr, nullptr}, launch_condense<16>, launch_score<16>, launch_assemble<16>},
     {20, {launch_solve<20, 2, 2>, launch_solve<20, 3, 1>, launch_solve_cluster<10, 2, 2, 3>}, launch_condense<20>, launch_score<20>, launch_assemble<20>},
-    {30, {launch_solve<30, 6, 1, 3>, launch_solve<30, 3, 1>, launch_solve_cluster<10, 3, 3, 2>, launch_solve<30, 6, 1, 2>, launch_solve<30, 3, 1, 2>}, launch_condense<30>, launch_score<30>, launch_assemble<30>},
+    {30, {launch_solve<30, 6, 1, 3>, launch_solve<30, 3, 1>, launch_solve_cluster<10, 3, 3, 2>, launch_solve<30, 6, 1, 2>, launch_solve<30, 3, 1, 2>}, launch_condense<30>, launch_score<30>, launch_assemble<30>, launch_solve<30, 6, 1, 3, true>},
     {40, {launch_solve_cluster<10, 4, 4, 1>, nullptr, nullptr}, nullptr, launch_score<40>, launch_assemble<40>},
     {60, {launch_solve_cluster<10, 6, 6, 1>, nullptr, nullptr}, nullptr, launch_score<60>, launch_assemble<60>},
 };
@@ -162,6 +168,7 @@ const HorizonEntry* find_horizon(int N) {
 
 SolveLaunch pick_solve(const cmpc_config& c) {
   const HorizonEntry* e = find_horizon(c.N);
+  if (c.cache_factorization && e->solve_cached) return e->solve_cached;
   const int v = (c.kernel_variant >= 0 && c.kernel_variant < 5) ? c.kernel_variant : 0;
   return e->solve[v] ? e->solve[v] : e->solve[0];
 }
@@ -193,6 +200,14 @@ void fill_solve_params(const cmpc_handle* h, cmpc::SolveParams& p) {
   p.adaptive_rho_tolerance = c.adaptive_rho_tolerance;
   p.rho_min = c.rho_min;
   p.rho_max = c.rho_max;
+  p.cache_pinv = h->d_cache_pinv;      // nullptr unless cfg.cache_factorization
+  p.cache_r = h->d_cache_r;
+  p.cache_mask = h->d_cache_mask;
+  p.cache_meta = h->d_cache_meta;
+  p.cache_tol_r = c.cache_tol_r;
+  p.cache_tol_yaw = c.cache_tol_yaw;
+  p.cache_max_iter = c.cache_max_iter;
+  p.cache_hit = h->d_cache_hit;
 }
 
 // Enqueue the LPT ordering of a batch (2 small kernels) and point p.order at it.
@@ -278,6 +293,10 @@ int cmpc_default_config(cmpc_config* cfg, int32_t N, int32_t max_batch) {
   cfg->lpt_schedule = 1024;             // hardest-first launch order for batches >= this size
   cfg->device = 0;
   cfg->host_zero_copy = 1;              // pinned caller buffers are accessed in place
+  cfg->cache_factorization = 0;         // closed-loop callers switch it on (rollout.py)
+  cfg->cache_tol_r = 2e-3f;
+  cfg->cache_tol_yaw = 2e-3f;
+  cfg->cache_max_iter = 30;
   return CMPC_OK;
 }
 
@@ -294,6 +313,8 @@ int cmpc_create(const cmpc_config* cfg, cmpc_handle** out) {
   if (c.max_iter < 0 || c.check_every <= 0 || c.refresh_every < 0)
     return fail(CMPC_ERR_INVALID, "max_iter >= 0, check_every > 0, refresh_every >= 0 required");
   if (c.warm_mode < 0 || c.warm_mode > 2) return fail(CMPC_ERR_INVALID, "bad warm_mode");
+  if (c.cache_factorization && (!(c.cache_tol_r >= 0.f) || !(c.cache_tol_yaw >= 0.f) || c.cache_max_iter < 0))
+    return fail(CMPC_ERR_INVALID, "cache tolerances and cache_max_iter must be >= 0");
   if (c.adaptive_rho_interval < 0 || (c.adaptive_rho_interval > 0 && !(c.adaptive_rho_tolerance > 1.f)))
     return fail(CMPC_ERR_INVALID, "adaptive_rho_interval >= 0 and adaptive_rho_tolerance > 1 required");
   if (!(c.rho_min > 0.f) || !(c.rho_min <= c.rho_max)) return fail(CMPC_ERR_INVALID, "0 < rho_min <= rho_max required");
@@ -366,6 +387,25 @@ int cmpc_create(const cmpc_config* cfg, cmpc_handle** out) {
     cmpc_destroy(h);
     return fail(CMPC_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
   }
+  if (c.cache_factorization && !find_horizon(N)->solve_cached) {
+    cmpc_destroy(h);
+    return fail(CMPC_ERR_UNSUPPORTED, "cache_factorization is compiled for N = 10 and N = 30 only");
+  }
+  if (c.cache_factorization) {
+    // a tile row is padded to a multiple of 4 SPLIT floats, SPLIT <= 6 in the compiled layouts
+    const size_t NW = 6 * (size_t)N, per_entry = NW * (NW + 20) * sizeof(float);
+    const size_t entries = slots;
+    if ((e = cudaMalloc(&h->d_cache_pinv, entries * per_entry)) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_cache_r, entries * 12 * N * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_cache_mask, entries * N)) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_cache_meta, entries * 4 * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_cache_hit, slots)) != cudaSuccess ||
+        (e = cudaMemset(h->d_cache_hit, 0, slots)) != cudaSuccess ||
+        (e = cudaMemset(h->d_cache_meta, 0, entries * 4 * sizeof(float))) != cudaSuccess) {
+      cmpc_destroy(h);
+      return fail(CMPC_ERR_CUDA, "factorisation cache allocation failed: %s", cudaGetErrorString(e));
+    }
+  }
   *out = h;
   return CMPC_OK;
 }
@@ -381,6 +421,11 @@ int cmpc_destroy(cmpc_handle* h) {
   cudaFree(h->d_score);
   cudaFree(h->d_order);
   cudaFree(h->d_hist);
+  cudaFree(h->d_cache_pinv);
+  cudaFree(h->d_cache_r);
+  cudaFree(h->d_cache_mask);
+  cudaFree(h->d_cache_meta);
+  cudaFree(h->d_cache_hit);
   if (h->st.h_in) cudaFreeHost(h->st.h_in);
   if (h->st.h_out) cudaFreeHost(h->st.h_out);
   cudaFree(h->st.d_in);
@@ -394,6 +439,32 @@ int cmpc_destroy(cmpc_handle* h) {
 }
 
 int64_t cmpc_launch_count(const cmpc_handle* h) { return h ? h->launches.load() : 0; }
+
+int cmpc_accumulate_stats(cmpc_handle* h, int32_t B, int32_t slot0, const int32_t* iters,
+                          const int32_t* status, uint64_t* acc, void* stream) {
+  int rc = check_batch(h, B, slot0);
+  if (rc) return rc;
+  if (B == 0) return CMPC_OK;
+  if (!iters || !status || !acc) return fail(CMPC_ERR_INVALID, "null pointer");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  cmpc::stats_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      iters, status, h->d_cache_hit ? h->d_cache_hit + slot0 : nullptr, B,
+      reinterpret_cast<unsigned long long*>(acc));
+  CUDA_TRY(cudaGetLastError());
+  h->launches.fetch_add(1);
+  return CMPC_OK;
+}
+
+int cmpc_get_cache_meta(cmpc_handle* h, int32_t B, int32_t slot0, float* meta, void* stream) {
+  int rc = check_batch(h, B, slot0);
+  if (rc) return rc;
+  if (!meta) return fail(CMPC_ERR_INVALID, "null pointer");
+  if (!h->d_cache_meta) return fail(CMPC_ERR_INVALID, "the handle was created without cache_factorization");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaMemcpyAsync(meta, h->d_cache_meta + (size_t)slot0 * 4, (size_t)B * 4 * sizeof(float),
+                           cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return CMPC_OK;
+}
 
 int cmpc_last_kernel_ms(cmpc_handle* h, float* ms) {
   if (!h || !ms) return fail(CMPC_ERR_INVALID, "null argument");
@@ -774,6 +845,7 @@ int cmpc_reset_warm(cmpc_handle* h, const uint8_t* slot_mask) {
   if (!h) return fail(CMPC_ERR_INVALID, "null handle");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   const size_t slots = (size_t)h->cfg.max_batch;
+  if (h->d_cache_meta) CUDA_TRY(cudaMemset(h->d_cache_meta, 0, slots * 4 * sizeof(float)));   // cached factors too
   if (!slot_mask) {
     CUDA_TRY(cudaMemset(h->d_warm_valid, 0, slots));
     return CMPC_OK;

@@ -57,6 +57,15 @@ struct SolveParams {
   float adaptive_rho_tolerance;
   float rho_min, rho_max;             // clamp of the adapted rho (fp32 stability of the Woodbury form)
   long long* dbg_clk;                 // debug: phase timestamps of CTA 0 (nullptr in production)
+  // factorisation cache (closed-loop use, cfg.cache_factorization): -P^-1 of each slot's last
+  // factorisation with the data it was computed for; nullptr = off
+  float4* __restrict__ cache_pinv;    // [slots][NW*NWP/4 float4], laid out [tile piece][thread]
+  float* __restrict__ cache_r;        // [slots][12 N] lever arms of that factorisation
+  uint8_t* __restrict__ cache_mask;   // [slots][N]
+  float* __restrict__ cache_meta;     // [slots][4]: rho, yaw, valid, reused by the last launch
+  float cache_tol_r, cache_tol_yaw;
+  int32_t cache_max_iter;             // a solve that needs more iterations invalidates its cache entry
+  uint8_t* __restrict__ cache_hit;         // [slots] 1 if the last launch reused a cached factor
 };
 
 // Thread geometry.  Every "row thread" owns R rows of P (rows rp + q*NWR, q < R: same axis,
@@ -176,7 +185,9 @@ __device__ __forceinline__ float wrench_linear_term(int j, int a, const float* s
 // ---------------------------------------------------------------------------------------
 // Fused condense + factor + ADMM kernel.  One CTA per problem.
 // ---------------------------------------------------------------------------------------
-template <int N, int SPLIT, int MINB, int R>
+// CACHE compiles the factorisation cache in (closed-loop instantiations); the default
+// instantiation carries none of its state through the register-limited ADMM loop.
+template <int N, int SPLIT, int MINB, int R, bool CACHE>
 __global__ void __launch_bounds__((Geo<N, SPLIT, R>::THREADS), MINB)
 solve_kernel(const SolveParams p) {
   using G_ = Geo<N, SPLIT, R>;
@@ -232,6 +243,24 @@ solve_kernel(const SolveParams p) {
   __syncthreads();
 
   if (p.dbg_clk && blockIdx.x == 0 && tid == 0) p.dbg_clk[1] = clock64();
+  // Factorisation cache: P depends on the lever arms, the contact masks, the yaw and rho only.
+  // When none of them moved (a standing robot, or any stretch with a static contact schedule),
+  // the cached -P^-1 is reused as is: the iteration is in residual-correction form, so an
+  // inexact K^-1 changes the convergence rate but not the fixed point or the stopping test.
+  bool reuse = false;
+  const size_t cslot = (size_t)slot;
+  if (CACHE && p.cache_pinv) {
+    const float* meta = p.cache_meta + cslot * 4;
+    bool ok = meta[2] != 0.f && meta[0] == p.rho && fabsf(meta[1] - s_x0[2]) <= p.cache_tol_yaw;
+    for (int i = tid; i < 3 * NLEG; i += THREADS)
+      ok = ok && fabsf(s_r[i] - p.cache_r[cslot * 3 * NLEG + i]) <= p.cache_tol_r;
+    for (int i = tid; i < N; i += THREADS) ok = ok && s_mask[i] == (int)p.cache_mask[cslot * N + i];
+    reuse = __syncthreads_and(ok) != 0;
+    if (tid == 0) { p.cache_meta[cslot * 4 + 3] = reuse ? 1.f : 0.f; p.cache_hit[slot] = reuse ? 1 : 0; }
+  }
+  bool cached_fresh = false;          // this launch stored a new factorisation of the CURRENT data
+  bool used_cache = false;            // the iteration runs on a reused (possibly slightly stale) factor
+
   float sn, cs;
   sincosf(s_x0[2], &sn, &cs);
   const float im = p.inv_mass;
@@ -289,11 +318,27 @@ solve_kernel(const SolveParams p) {
   if (p.dbg_clk && blockIdx.x == 0 && tid == 0) p.dbg_clk[2] = clock64();
   // ---- phases 2+3 as a re-runnable step (adaptive rho refactorises) ------------------------
   float row[R][COLS];
+  constexpr int TILE4 = R * COLS / 4;                   // 16-byte pieces of a thread's tile
   auto factorize = [&]() {
   // d of this leg for the current rho (K = H + (sigma + rho) I on the stance forces)
   dinv = stance ? 1.f / (p.sigma + 2.f * p.r_weight + rho) : 0.f;
   if (is_leg) s_G[tid][9] = dinv;
   __syncthreads();
+  if (reuse) {                                          // CTA-uniform; only the first call can hit
+    reuse = false;
+    used_cache = true;
+    if (is_row) {
+      const float4* src = p.cache_pinv + cslot * TILE4 * G_::ROWT + tid;
+#pragma unroll
+      for (int q = 0; q < R; ++q)
+#pragma unroll
+        for (int c = 0; c < COLS; c += 4) {
+          const float4 v = __ldg(src + (size_t)((q * COLS + c) / 4) * G_::ROWT);
+          row[q][c] = v.x; row[q][c + 1] = v.y; row[q][c + 2] = v.z; row[q][c + 3] = v.w;
+        }
+    }
+    return;
+  }
   // ---- phase 2: P = M^-1 + E (R x COLS register tiles) -------------------------------------
   // E_j[ra][a'] = sum_l sum_c Gp[ra][c] d Gp[a'][c],  Gp = [Ghat ; I/m]
   float E[R][6];
@@ -446,6 +491,18 @@ solve_kernel(const SolveParams p) {
         const float v = col == rp + q * NWR ? diag[q] : row[q][c];
         row[q][c] = v * sc[q] * (col < NW ? s_S[col] : 0.f);
       }
+    if (CACHE && p.cache_pinv) {
+      float4* dst = p.cache_pinv + cslot * TILE4 * G_::ROWT + tid;
+#pragma unroll
+      for (int q = 0; q < R; ++q)
+#pragma unroll
+        for (int c = 0; c < COLS; c += 4)
+          dst[(size_t)((q * COLS + c) / 4) * G_::ROWT] = make_float4(row[q][c], row[q][c + 1], row[q][c + 2], row[q][c + 3]);
+    }
+  }
+  if (CACHE && p.cache_pinv) {
+    cached_fresh = true;
+    if (tid == 0) p.cache_meta[cslot * 4] = rho;   // the cached factor belongs to this rho
   }
   __syncthreads();
   };
@@ -475,20 +532,25 @@ solve_kernel(const SolveParams p) {
   float gl[3] = {0.f, 0.f, 0.f};          // linear term of this leg:  G' h
   float hj[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // h of this stage
   float vh[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // v + h,  v = M G x  (wrench-space gradient)
-  if (is_leg && stance) {
+  auto init_iterate = [&]() {
+    if (is_leg && stance) {
 #pragma unroll
-    for (int a = 0; a < 6; ++a) hj[a] = s_h[6 * lj + a];
+      for (int a = 0; a < 6; ++a) hj[a] = s_h[6 * lj + a];
 #pragma unroll
-    for (int k = 0; k < 3; ++k)
-      gl[k] = Gh[0][k] * hj[0] + Gh[1][k] * hj[1] + Gh[2][k] * hj[2] + im * hj[3 + k];
-    if (warm) {
-      x[0] = wx_in[0]; x[1] = wx_in[1]; x[2] = wx_in[2];
-      y[0] = wy_in[0]; y[1] = wy_in[1]; y[2] = wy_in[2];
+      for (int k = 0; k < 3; ++k)
+        gl[k] = Gh[0][k] * hj[0] + Gh[1][k] * hj[1] + Gh[2][k] * hj[2] + im * hj[3 + k];
+      x[0] = x[1] = x[2] = 0.f;
+      y[0] = y[1] = y[2] = 0.f;
+      if (warm) {
+        x[0] = wx_in[0]; x[1] = wx_in[1]; x[2] = wx_in[2];
+        y[0] = wy_in[0]; y[1] = wy_in[1]; y[2] = wy_in[2];
+      }
+      project(x[0], x[1], x[2], z[0], z[1], z[2]);
     }
-    project(x[0], x[1], x[2], z[0], z[1], z[2]);
-  }
 #pragma unroll
-  for (int a = 0; a < 6; ++a) vh[a] = hj[a];
+    for (int a = 0; a < 6; ++a) vh[a] = hj[a];
+  };
+  init_iterate();
 
   // exact wrench-space gradient  v = M (G x)  (uniform: every thread takes part)
   auto refresh_gradient = [&]() {
@@ -611,22 +673,42 @@ solve_kernel(const SolveParams p) {
       dua = m1;
       const float eps_p = p.eps_abs + p.eps_rel * m2;
       const float eps_d = p.eps_abs + p.eps_rel * fmaxf(m3, ng);
-      if (!(m4 == 0.f) || !(m0 == m0) || !(m1 == m1)) { status = -1; break; }
-      if (pri <= eps_p && dua <= eps_d) { status = 1; break; }
-      if (it >= p.max_iter) { status = 0; break; }
-      if (adapt_now) {
-        // OSQP's rho adaptation: balance the normalised primal and dual residuals
-        const float pr_n = m0 / (m2 + 1e-10f);
-        const float du_n = m1 / (fmaxf(m3, ng) + 1e-10f);
-        float rn = rho * sqrtf(pr_n / (du_n + 1e-10f));
-        rn = fminf(fmaxf(rn, p.rho_min), p.rho_max);
-        if (rn > rho * p.adaptive_rho_tolerance || rn * p.adaptive_rho_tolerance < rho) {
-          rho = rn;
-          rho_inv = 1.f / rho;
-          ++rho_updates;
-          factorize();     // uniform: every thread of the CTA sees the same statistics
-          continue;        // redo phase A of this iterate with the new rho
+      const bool nonfinite = !(m4 == 0.f) || !(m0 == m0) || !(m1 == m1);
+      const bool converged = pri <= eps_p && dua <= eps_d;
+      // a reused factor that is too stale for this problem (slow or blown up): factorise the
+      // current data and go on.  Shares the one in-loop factorize() call with the rho adaptation.
+      const bool stale = used_cache && !converged && (nonfinite || it >= p.cache_max_iter);
+      bool refactor = stale;
+      if (stale) {
+        used_cache = false;
+        if (nonfinite) {                       // restart from the cold iterate: x = y = 0, v = 0
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { x[k] = 0.f; y[k] = 0.f; z[k] = 0.f; }
+          if (is_leg && stance) project(0.f, 0.f, 0.f, z[0], z[1], z[2]);
+#pragma unroll
+          for (int a = 0; a < 6; ++a) vh[a] = hj[a];
         }
+      } else {
+        if (nonfinite) { status = -1; break; }
+        if (converged) { status = 1; break; }
+        if (it >= p.max_iter) { status = 0; break; }
+        if (adapt_now) {
+          // OSQP's rho adaptation: balance the normalised primal and dual residuals
+          const float pr_n = m0 / (m2 + 1e-10f);
+          const float du_n = m1 / (fmaxf(m3, ng) + 1e-10f);
+          float rn = rho * sqrtf(pr_n / (du_n + 1e-10f));
+          rn = fminf(fmaxf(rn, p.rho_min), p.rho_max);
+          if (rn > rho * p.adaptive_rho_tolerance || rn * p.adaptive_rho_tolerance < rho) {
+            rho = rn;
+            rho_inv = 1.f / rho;
+            ++rho_updates;
+            refactor = true;
+          }
+        }
+      }
+      if (refactor) {
+        factorize();     // uniform: every thread of the CTA sees the same statistics
+        continue;        // redo phase A of this iterate with the new factor
       }
     }
     // wrench phase: q = P^-1 s   (row holds -P^-1); each slice publishes its partial sum
@@ -688,6 +770,19 @@ solve_kernel(const SolveParams p) {
     wx[0] = x[0]; wx[1] = x[1]; wx[2] = x[2];
     float* wy = p.warm_y + ((size_t)slot * NLEG + tid) * 3;
     wy[0] = y[0]; wy[1] = y[1]; wy[2] = y[2];
+  }
+  if (CACHE && p.cache_pinv) {
+    if (cached_fresh) {
+      for (int i = tid; i < 3 * NLEG; i += THREADS) p.cache_r[cslot * 3 * NLEG + i] = s_r[i];
+      for (int i = tid; i < N; i += THREADS) p.cache_mask[cslot * N + i] = (uint8_t)s_mask[i];
+    }
+    if (tid == 0) {
+      float* meta = p.cache_meta + cslot * 4;
+      if (cached_fresh) meta[1] = s_x0[2];
+      // keep the entry only for healthy solves: a slow or failed one refactorises next time
+      const bool keep = status == 1 && it <= p.cache_max_iter && (cached_fresh || meta[2] != 0.f);
+      meta[2] = keep ? 1.f : 0.f;
+    }
   }
   if (tid == 0) {
     if (p.iters) p.iters[b] = it;
@@ -1082,6 +1177,29 @@ __global__ void __launch_bounds__(128) plant_kernel(const PlantParams p) {
 }
 
 __global__ void tick_kernel(int32_t* tick) { *tick += 1; }
+
+// Running totals of a closed-loop rollout in one launch: ADMM iterations, problems whose status
+// is not "solved", factorisation-cache hits (meta may be nullptr).  acc[3], unsigned 64-bit.
+__global__ void __launch_bounds__(256) stats_kernel(const int32_t* __restrict__ iters,
+                                                    const int32_t* __restrict__ status,
+                                                    const uint8_t* __restrict__ hitflag, int32_t B,
+                                                    unsigned long long* __restrict__ acc) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned it = 0, bad = 0, hit = 0;
+  if (b < B) {
+    it = (unsigned)iters[b];
+    bad = status[b] != 1;
+    hit = hitflag ? (unsigned)hitflag[b] : 0u;
+  }
+  it = __reduce_add_sync(0xffffffffu, it);
+  bad = __reduce_add_sync(0xffffffffu, bad);
+  hit = __reduce_add_sync(0xffffffffu, hit);
+  if ((threadIdx.x & 31) == 0) {
+    if (it) atomicAdd(acc, (unsigned long long)it);
+    if (bad) atomicAdd(acc + 1, (unsigned long long)bad);
+    if (hit) atomicAdd(acc + 2, (unsigned long long)hit);
+  }
+}
 
 // ---------------------------------------------------------------------------------------
 // Leg controllers on the output side of the MPC: one thread per

@@ -63,7 +63,10 @@ class ClosedLoopRollout:
         self.x_des = torch.empty((B, N + 1, 13), dtype=torch.float32, device=dev)
         self.r = torch.empty((B, N, 4, 3), dtype=torch.float32, device=dev)
         self.mask = torch.empty((B, N), dtype=torch.uint8, device=dev)
-        opts = dict(warm_mode=1)
+        # closed-loop defaults: reference warm start; no hardest-first scheduling (warm-started ticks
+        # have uniform iteration counts: the two scheduling kernels only cost time, measured 0.372 ->
+        # 0.355 ms per tick); factorisation cache (standing phases reuse -P^-1: 0.355 -> 0.295 ms)
+        opts = dict(warm_mode=1, lpt_schedule=0, cache_factorization=1 if self.N in (10, 30) else 0)
         opts.update(solver_options)
         self.mpc = BatchedMPC(N=N, max_batch=B, device=device, **opts)
         self.out = self.mpc.alloc_outputs(B, want_X=False, device=dev)
@@ -72,8 +75,7 @@ class ClosedLoopRollout:
             ds=self.ds.data_ptr(), v_ref=self.v_ref.data_ptr(), omega_ref=self.omega_ref.data_ptr(),
             rp0=self.rp0.data_ptr(), S=self.plan.n_steps, total_steps=total_steps,
             step_height=float(self.plan.step_height), g=GRAVITY)
-        self.iters_sum = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.unsolved = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.acc = torch.zeros(3, dtype=torch.int64, device=dev)   # iterations, unsolved, cache hits
         self._graph = None
 
     # one tick on the current stream -----------------------------------------------------
@@ -91,8 +93,9 @@ class ClosedLoopRollout:
                                       _ptr(self.track_err), s))
 
     def accumulate_stats(self):
-        self.iters_sum += self.out[2].sum()
-        self.unsolved += (self.out[5] != 1).sum()
+        s = C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+        _capi.check(_capi.lib().cmpc_accumulate_stats(self.mpc._h, self.B, 0, _ptr(self.out[2]),
+                                                      _ptr(self.out[5]), _ptr(self.acc), s))
 
     def capture(self, ticks_per_graph=10):
         """Capture `ticks_per_graph` ticks in a CUDA graph (static launch sequence)."""
@@ -130,5 +133,6 @@ class ClosedLoopRollout:
         te = self.track_err.cpu().numpy() / max(t, 1)
         return dict(ticks=t, com_z_min=float(x[:, 5].min()), com_z_max=float(x[:, 5].max()),
                     rms_pos_err=float(np.sqrt(te[:, 0].mean())), rms_ang_err=float(np.sqrt(te[:, 1].mean())),
-                    mean_iters=float(self.iters_sum.item()) / max(t * self.B, 1),
-                    unsolved=int(self.unsolved.item()), finite=bool(np.isfinite(x).all()))
+                    mean_iters=float(self.acc[0].item()) / max(t * self.B, 1),
+                    cache_hit_frac=float(self.acc[2].item()) / max(t * self.B, 1),
+                    unsolved=int(self.acc[1].item()), finite=bool(np.isfinite(x).all()))

@@ -173,6 +173,14 @@ class BatchedMPC:
         _capi.check(_capi.lib().cmpc_set_warm(self._h, x.shape[0], slot0, _ptr(x), _ptr(y),
                                               C.c_void_p(s)))
 
+    def cache_meta(self, B, slot0=0):
+        """[B,4] device tensor {rho, yaw, valid, reused-by-last-solve} of the factorisation cache."""
+        import torch
+        out = torch.empty((B, 4), dtype=torch.float32, device=torch.device("cuda", self.device))
+        s = torch.cuda.current_stream(out.device).cuda_stream
+        _capi.check(_capi.lib().cmpc_get_cache_meta(self._h, B, slot0, _ptr(out), C.c_void_p(s)))
+        return out
+
     @property
     def last_kernel_ms(self) -> float:
         """Duration of the solve kernel of the last :meth:`solve` (needs ``time_kernel=1``)."""

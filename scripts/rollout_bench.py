@@ -5,8 +5,16 @@ import torch
 import mpc_b200 as pkg
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
-for warm_mode, graph in ((1, True), (2, True), (1, False)):
-    ro = pkg.ClosedLoopRollout(B, N=10, gaits=("trot",), mu=(0.3, 1.0), seed=0, warm_mode=warm_mode)
+CASES = [  # warm_mode, cuda graph, solver options (ClosedLoopRollout defaults: lpt_schedule=0, cache_factorization=1)
+    (1, True, dict()),
+    (1, True, dict(cache_factorization=0)),
+    (1, True, dict(cache_factorization=0, lpt_schedule=1024)),
+    (1, True, dict(cache_tol_r=2e-2, cache_tol_yaw=2e-2)),     # far too loose: the in-kernel fallback refactorises
+    (2, True, dict()),
+    (1, False, dict()),
+]
+for warm_mode, graph, opts in CASES:
+    ro = pkg.ClosedLoopRollout(B, N=10, gaits=("trot",), mu=(0.3, 1.0), seed=0, warm_mode=warm_mode, **opts)
     ro.run(21, use_graph=graph, ticks_per_graph=20)       # warm-up + capture
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -15,6 +23,6 @@ for warm_mode, graph in ((1, True), (2, True), (1, False)):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     s = ro.summary()
-    print(json.dumps(dict(config="closed loop, %d robots x %d ticks, trot, mu 0.3-1.0" % (B, done), warm_mode=warm_mode,
+    print(json.dumps(dict(config="closed loop, %d robots x %d ticks, trot, mu 0.3-1.0" % (B, done), warm_mode=warm_mode, solver_options=opts,
                           cuda_graph=graph, ms_per_tick=ms / done, robot_ticks_per_s=B * done / (ms * 1e-3),
                           wall_s=time.perf_counter() - t0, **s)), flush=True)

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 import mpc_b200 as pkg                                             # noqa: E402
 from mpc_b200 import _capi                                         # noqa: E402
-from mpc_b200.problems import GAIT_NAMES, DT, GRAVITY              # noqa: E402
+from mpc_b200.problems import GAIT_NAMES, DT, GRAVITY, synthetic_batch   # noqa: E402
 from mpc_b200.solver import _ptr                                   # noqa: E402
 from oracle import condensed_admm as ca, srbd_qp                    # noqa: E402
 
@@ -159,3 +159,66 @@ def test_log_export_has_the_reference_schema(tmp_path, gold):
     assert set(log["sim_params"]) >= {"g", "h", "ss_duration", "ds_duration", "first_swing", "µ", "N",
                                       "v_com_ref", "theta_dot", "total_steps", "world_time_step"}
     assert log["mpc_freq"] > 1000.0          # solves per second of the single robot's tick
+
+
+def test_factorisation_cache_reuses_on_static_data_and_keeps_the_answers():
+    """cfg.cache_factorization: a second solve of the same problems reuses the cached -P^-1 (no
+    sweep) and returns the same converged forces; moving a lever arm beyond the tolerance, flipping
+    a contact bit or resetting the warm state forces a fresh factorisation."""
+    pb = synthetic_batch(256, N=10, gaits=GAIT_NAMES, seed=21)
+    args = [torch.from_numpy(a).cuda() for a in pb.f32()]
+    ref = pkg.BatchedMPC(N=10, max_batch=256, warm_mode=0)
+    U0, X0, s0 = ref.solve(*args)
+    mpc = pkg.BatchedMPC(N=10, max_batch=256, warm_mode=0, cache_factorization=1, cache_max_iter=1000)
+    U1, X1, s1 = mpc.solve(*args)
+    m1 = mpc.cache_meta(256).cpu().numpy()
+    assert np.all(m1[:, 3] == 0)                                    # nothing cached yet
+    assert torch.equal(U1, U0) and torch.equal(s1.iters, s0.iters)  # a miss is the plain path, bit for bit
+    U2, X2, s2 = mpc.solve(*args)
+    m2 = mpc.cache_meta(256).cpu().numpy()
+    ok = s1.status.cpu().numpy() == 1
+    adapted = m1[:, 0] != np.float32(mpc.cfg.rho)                   # rho was adapted: cached factor is for another rho
+    assert np.all(m2[ok & ~adapted, 3] == 1) and np.all(m2[adapted, 3] == 0)
+    assert torch.equal(U2, U1) and torch.equal(s2.iters, s1.iters)  # same factor, same iterates
+    # a lever arm moved by 1 mm stays inside the tolerance: reused, answers within the solver tolerance
+    moved = [a.clone() for a in args]
+    moved[1][:, 3, 1, 0] += 1e-3
+    U3, X3, s3 = mpc.solve(*moved)
+    m3 = mpc.cache_meta(256).cpu().numpy()
+    assert np.all(m3[ok & ~adapted, 3] == 1)
+    U3f, X3f, s3f = ref.solve(*moved)
+    good = (s3.status == 1) & (s3f.status == 1)
+    assert float(good.float().mean()) > 0.99
+    J = lambda X, xd: ((X[:, :, :12] - xd[:, :, :12]) ** 2 * torch.tensor(
+        [1e4, 2.7e4, 1e4, 2.7e5, 2.7e5, 2.7e5, 1e4, 1e4, 1e4, 1.6e4, 1.6e4, 1.6e4], device=X.device)).sum((1, 2))
+    rel = (J(X3, moved[3]) / J(X3f, moved[3]) - 1).abs()[good]
+    assert float(rel.max()) < 2e-2                                   # both within eps of the same optimum
+    # 5 mm: outside the tolerance -> fresh factorisation, identical to the plain solver
+    moved[1][:, 3, 1, 0] += 4e-3
+    U4, _, s4 = mpc.solve(*moved)
+    assert np.all(mpc.cache_meta(256).cpu().numpy()[:, 3] == 0)
+    U4f, _, s4f = ref.solve(*moved)
+    assert torch.equal(U4, U4f) and torch.equal(s4.iters, s4f.iters)
+    # a flipped contact bit -> miss; reset_warm drops the cache
+    flipped = [a.clone() for a in moved]
+    flipped[2][:, 5] ^= 1
+    mpc.solve(*flipped)
+    assert np.all(mpc.cache_meta(256).cpu().numpy()[:, 3] == 0)
+    mpc.solve(*flipped)
+    assert np.mean(mpc.cache_meta(256).cpu().numpy()[:, 3]) > 0.8
+    mpc.reset_warm()
+    mpc.solve(*flipped)
+    assert np.all(mpc.cache_meta(256).cpu().numpy()[:, 3] == 0)
+
+
+def test_closed_loop_with_factorisation_cache_tracks_like_without():
+    a = pkg.ClosedLoopRollout(256, N=10, gaits=("trot",), mu=(0.3, 1.0), seed=0, total_steps=4, cache_factorization=0)
+    b = pkg.ClosedLoopRollout(256, N=10, gaits=("trot",), mu=(0.3, 1.0), seed=0, total_steps=4, cache_factorization=1)
+    a.run(200, use_graph=False)
+    b.run(200, use_graph=False)
+    sa, sb = a.summary(), b.summary()
+    assert sa["unsolved"] == 0 and sb["unsolved"] == 0 and sb["finite"]
+    assert sb["cache_hit_frac"] > 0.3                    # the standing phase after the 4 planned steps
+    assert abs(sb["rms_pos_err"] - sa["rms_pos_err"]) < 2e-4 and abs(sb["rms_ang_err"] - sa["rms_ang_err"]) < 5e-4
+    xa, xb = a.x.cpu().numpy(), b.x.cpu().numpy()
+    assert np.abs(xa[:, :12] - xb[:, :12]).max() < 2e-3

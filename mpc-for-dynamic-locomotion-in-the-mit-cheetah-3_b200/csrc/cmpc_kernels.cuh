@@ -206,6 +206,7 @@ solve_kernel(const SolveParams p) {
   __shared__ __align__(16) float s_h[NWP];             // linear term h
   __shared__ __align__(16) float s_S[NWP];             // Jacobi scaling 1/sqrt(P_ii) of the sweep
   __shared__ float s_red[2][LWARPS][8];
+  __shared__ float s_gl[3 * NLEG];                      // G' h per leg (read at check iterations only)
   __shared__ float s_pre[2][6 * (N + 1)];              // prefix sums for the X output
   __shared__ int s_mask[N];
 
@@ -529,26 +530,31 @@ solve_kernel(const SolveParams p) {
   float x[3] = {0.f, 0.f, 0.f};
   float y[3] = {0.f, 0.f, 0.f};
   float z[3] = {0.f, 0.f, 0.f};
-  float gl[3] = {0.f, 0.f, 0.f};          // linear term of this leg:  G' h
-  float hj[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // h of this stage
   float vh[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // v + h,  v = M G x  (wrench-space gradient)
+  float glmax = 0.f;                               // max |G' h| of this leg (G' h itself lives in s_gl)
   auto init_iterate = [&]() {
-    if (is_leg && stance) {
 #pragma unroll
-      for (int a = 0; a < 6; ++a) hj[a] = s_h[6 * lj + a];
+    for (int a = 0; a < 6; ++a) vh[a] = 0.f;
+    if (is_leg) {
+      float gl[3] = {0.f, 0.f, 0.f};               // linear term of this leg:  G' h
+      if (stance) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k)
-        gl[k] = Gh[0][k] * hj[0] + Gh[1][k] * hj[1] + Gh[2][k] * hj[2] + im * hj[3 + k];
-      x[0] = x[1] = x[2] = 0.f;
-      y[0] = y[1] = y[2] = 0.f;
-      if (warm) {
-        x[0] = wx_in[0]; x[1] = wx_in[1]; x[2] = wx_in[2];
-        y[0] = wy_in[0]; y[1] = wy_in[1]; y[2] = wy_in[2];
+        for (int a = 0; a < 6; ++a) vh[a] = s_h[6 * lj + a];     // h of this stage (v = 0 at x = 0)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          gl[k] = Gh[0][k] * vh[0] + Gh[1][k] * vh[1] + Gh[2][k] * vh[2] + im * vh[3 + k];
+        x[0] = x[1] = x[2] = 0.f;
+        y[0] = y[1] = y[2] = 0.f;
+        if (warm) {
+          x[0] = wx_in[0]; x[1] = wx_in[1]; x[2] = wx_in[2];
+          y[0] = wy_in[0]; y[1] = wy_in[1]; y[2] = wy_in[2];
+        }
+        project(x[0], x[1], x[2], z[0], z[1], z[2]);
       }
-      project(x[0], x[1], x[2], z[0], z[1], z[2]);
-    }
 #pragma unroll
-    for (int a = 0; a < 6; ++a) vh[a] = hj[a];
+      for (int k = 0; k < 3; ++k) s_gl[3 * tid + k] = gl[k];   // only this thread reads it back
+      glmax = fmaxf(fabsf(gl[0]), fmaxf(fabsf(gl[1]), fabsf(gl[2])));
+    }
   };
   init_iterate();
 
@@ -576,7 +582,7 @@ solve_kernel(const SolveParams p) {
     __syncthreads();
     if (is_leg && stance) {
 #pragma unroll
-      for (int a = 0; a < 6; ++a) vh[a] = s_v[6 * lj + a] + hj[a];
+      for (int a = 0; a < 6; ++a) vh[a] = s_v[6 * lj + a] + s_h[6 * lj + a];
     }
     __syncthreads();
   };
@@ -585,7 +591,7 @@ solve_kernel(const SolveParams p) {
   // constant part of the dual tolerance: ||G' h||_inf
   float ng = 0.f;
   {
-    float m = fmaxf(fabsf(gl[0]), fmaxf(fabsf(gl[1]), fabsf(gl[2])));
+    float m = glmax;
     if (leg_warp) {
       m = warp_max_nonneg(m);
       if (lane == 0) s_red[1][warp][0] = m;
@@ -645,7 +651,7 @@ solve_kernel(const SolveParams p) {
             m0 = fmaxf(m0, fabsf(rp[k]));                                   // primal residual
             m1 = fmaxf(m1, fabsf(rd));                                      // dual residual
             m2 = fmaxf(m2, fmaxf(fabsf(x[k]), fabsf(z[k])));                // max(|x|,|z|)
-            m3 = fmaxf(m3, fmaxf(fabsf(gr[k] - gl[k]), fabsf(y[k])));       // max(|Hx|,|y|)
+            m3 = fmaxf(m3, fmaxf(fabsf(gr[k] - s_gl[3 * tid + k]), fabsf(y[k])));       // max(|Hx|,|y|)
             sum += x[k] + rd;
           }
         }
@@ -686,7 +692,7 @@ solve_kernel(const SolveParams p) {
           for (int k = 0; k < 3; ++k) { x[k] = 0.f; y[k] = 0.f; z[k] = 0.f; }
           if (is_leg && stance) project(0.f, 0.f, 0.f, z[0], z[1], z[2]);
 #pragma unroll
-          for (int a = 0; a < 6; ++a) vh[a] = hj[a];
+          for (int a = 0; a < 6; ++a) vh[a] = (is_leg && stance) ? s_h[6 * lj + a] : 0.f;
         }
       } else {
         if (nonfinite) { status = -1; break; }

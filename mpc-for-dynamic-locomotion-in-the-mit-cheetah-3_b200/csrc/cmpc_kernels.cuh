@@ -206,6 +206,7 @@ solve_kernel(const SolveParams p) {
   __shared__ __align__(16) float s_h[NWP];             // linear term h
   __shared__ __align__(16) float s_S[NWP];             // Jacobi scaling 1/sqrt(P_ii) of the sweep
   __shared__ float s_red[2][LWARPS][8];
+  __shared__ __align__(8) float s_dump[2 * THREADS];   // scratch target of lanes that own no wrench pair
   __shared__ float s_gl[3 * NLEG];                      // G' h per leg (read at check iterations only)
   __shared__ float s_pre[2][6 * (N + 1)];              // prefix sums for the X output
   __shared__ int s_mask[N];
@@ -567,8 +568,7 @@ solve_kernel(const SolveParams p) {
         wv[a] = quad_sum(Gh[a][0] * x[0] + Gh[a][1] * x[1] + Gh[a][2] * x[2]);
 #pragma unroll
       for (int k = 0; k < 3; ++k) wv[3 + k] = quad_sum(x[k] * im);
-      if (is_leg && ll < 3)
-        *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = pick_pair(wv, ll);
+      *reinterpret_cast<float2*>((is_leg && ll < 3) ? s_s + 6 * lj + 2 * ll : s_dump + 2 * tid) = pick_pair(wv, ll);
     }
     __syncthreads();
     for (int i = tid; i < NW; i += THREADS) {
@@ -640,8 +640,8 @@ solve_kernel(const SolveParams p) {
         sv[a] = quad_sum(Gh[a][0] * t[0] + Gh[a][1] * t[1] + Gh[a][2] * t[2]);
 #pragma unroll
       for (int k = 0; k < 3; ++k) sv[3 + k] = quad_sum(t[k] * im);
-      if (is_leg && ll < 3)
-        *reinterpret_cast<float2*>(s_s + 6 * lj + 2 * ll) = pick_pair(sv, ll);
+      // every lane stores (no branch on the critical path): lanes without a pair hit the scratch row
+      *reinterpret_cast<float2*>((is_leg && ll < 3) ? s_s + 6 * lj + 2 * ll : s_dump + 2 * tid) = pick_pair(sv, ll);
       if (chk) {
         float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, sum = 0.f;
         if (stance) {
@@ -739,14 +739,17 @@ solve_kernel(const SolveParams p) {
         s_q[rs][rp + q * NWR] = -((acc[q][0] + acc[q][1]) + (acc[q][2] + acc[q][3]));
     }
     __syncthreads();
-    // leg phase B: x-update, relaxed projection, dual update
-    if (is_leg && stance) {
+    // leg phase B: x-update, relaxed projection, dual update.  Whole leg warps run it without a
+    // divergent branch: swing legs and padding lanes carry zero state (d = 0, G = 0), so the same
+    // instruction stream leaves their x and y at 0; only z is masked after the projection.
+    if (leg_warp) {
+      const int lq = is_leg ? 6 * lj : 0;
       float qv[6];
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
-        float acc = s_q[0][6 * lj + a];
+        float acc = s_q[0][lq + a];
 #pragma unroll
-        for (int sl = 1; sl < SPLIT; ++sl) acc += s_q[sl][6 * lj + a];
+        for (int sl = 1; sl < SPLIT; ++sl) acc += s_q[sl][lq + a];
         qv[a] = acc;
       }
 #pragma unroll
@@ -762,7 +765,10 @@ solve_kernel(const SolveParams p) {
       }
       project(w3[0], w3[1], w3[2], z[0], z[1], z[2]);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) y[k] = rho * (w3[k] - z[k]);
+      for (int k = 0; k < 3; ++k) {
+        z[k] = stance ? z[k] : 0.f;
+        y[k] = rho * (w3[k] - z[k]);
+      }
     }
     ++it;
   }

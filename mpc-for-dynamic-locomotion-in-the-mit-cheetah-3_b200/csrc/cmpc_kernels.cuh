@@ -584,7 +584,7 @@ solve_kernel(const SolveParams p) {
 #pragma unroll
       for (int a = 0; a < 6; ++a) vh[a] = s_v[6 * lj + a] + s_h[6 * lj + a];
     }
-    __syncthreads();
+    // no barrier here: s_v is next written by the next refresh, at least two barriers from now
   };
   if (warm) refresh_gradient();
 

@@ -165,19 +165,21 @@ GAIT_NAMES = ("trot", "pronk", "amble", "pseudo_gallop")
 
 
 def synthetic_batch(B, N=10, gaits=("trot",), seed=0, mu=(1.0, 1.0), tick_range=(20, 380),
-                    noise=1.0, total_steps=20) -> ProblemBatch:
+                    noise=1.0, total_steps=20, tick_shift=0) -> ProblemBatch:
     """Workload of BASELINE.json configs 2-4: robot b walks with gait
     ``gaits[b % len(gaits)]``... drawn uniformly; tick ~ U{tick_range}; velocity references
     v_x ~ U[-0.3,0.3], v_y ~ U[-0.1,0.1], yaw rate ~ U[-0.5,0.5]; measured state = reference
     state at that tick + N(0, sigma) noise (rpy 0.05 rad, com 0.02 m, omega 0.2 rad/s,
-    v 0.1 m/s); stage-0 feet = planned feet + N(0, 0.005 m); mu ~ U[mu]."""
+    v 0.1 m/s); stage-0 feet = planned feet + N(0, 0.005 m); mu ~ U[mu].
+    ``tick_shift`` moves every robot's tick by that many ticks with all random draws unchanged
+    (``tick_shift=-1`` is "the same problems one tick earlier", the warm-start source of config 2)."""
     rng = np.random.default_rng(seed)
     gid = rng.integers(0, len(gaits), size=B)
     table = [GAITS[g] for g in gaits]
     first_swing = np.array([table[i][0] for i in gid], dtype=np.int64)
     ss = np.array([table[i][1] for i in gid], dtype=np.int64)
     ds = np.array([table[i][2] for i in gid], dtype=np.int64)
-    tick = rng.integers(tick_range[0], tick_range[1], size=B)
+    tick = rng.integers(tick_range[0], tick_range[1], size=B) + int(tick_shift)
     v_ref = np.stack([rng.uniform(-0.3, 0.3, B), rng.uniform(-0.1, 0.1, B), np.zeros(B)], 1)
     om_ref = rng.uniform(-0.5, 0.5, B)
     mu_b = rng.uniform(mu[0], mu[1], B)

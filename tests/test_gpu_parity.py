@@ -317,24 +317,37 @@ def test_edge_cases():
         pkg.BatchedMPC(N=10, max_batch=4, w=[1, 1, 1, 1, 1, 1, 1, 2, 1, 1, 1, 1, 0])
 
 
-def test_full_size_properties_batch_4096():
-    """BASELINE.json config 2 at full size (4096 trot problems, N=10): size-independent
-    properties - all solved, dynamics consistency of the returned X with the returned U
-    (forward-Euler recursion of src/mpc.py:113-117 in fp64), permutation invariance."""
-    pb = synthetic_batch(4096, N=10, seed=0)
+@pytest.mark.parametrize("B,N,gaits,mu", [(4096, 10, ("trot",), (1.0, 1.0)),          # BASELINE config 2
+                                          (8192, 10, GAIT_NAMES, (0.3, 1.0)),           # config 3 (one GPU's shard), mu sweep
+                                          (16384, 30, ("trot",), (1.0, 1.0))])          # config 4
+def test_full_size_properties(B, N, gaits, mu):
+    """BASELINE.json configs at full per-GPU size: size-independent properties - all solved,
+    forces inside the reference's feasible set (src/mpc.py:148-173: swing forces exactly zero,
+    f_min <= fz <= f_max, |fx|,|fy| <= mu fz up to the solver tolerance), dynamics consistency of
+    the returned X with the returned U (forward-Euler recursion of src/mpc.py:113-117 in fp64),
+    permutation invariance (the property the hardest-first schedule and the sharding rely on)."""
+    pb = synthetic_batch(B, N=N, gaits=gaits, seed=0, mu=mu)
     out = gpu_solve(pb, warm_mode=0)
     assert np.all(out["status"] == 1)
+    U = out["U"].reshape(B, N, 4, 3)
+    st = pb.stance.astype(bool)                                      # (B,N,4)
+    assert np.all(U[~st] == 0.0)
+    fz, fx, fy = U[..., 2][st], U[..., 0][st], U[..., 1][st]
+    mu_b = np.broadcast_to(pb.mu[:, None, None], st.shape)[st]
+    tol = 1e-3 * 100.0 + 1e-3                                        # eps_rel * f_max + eps_abs on x - z
+    assert fz.min() >= 3.0 - tol and fz.max() <= 100.0 + tol
+    assert np.all(np.abs(fx) <= mu_b * fz + 2 * tol) and np.all(np.abs(fy) <= mu_b * fz + 2 * tol)
     rng = np.random.default_rng(0)
-    for b in rng.integers(0, 4096, 12):
-        x0, r, stance, xd, mu = pb.problem(b)
+    for b in rng.integers(0, B, 8):
+        x0, r, stance, xd, mu_ = pb.problem(b)
         x0, r = np.float32(x0).astype(np.float64), np.float32(r).astype(np.float64)
-        X = np.zeros((13, 11))
+        X = np.zeros((13, N + 1))
         X[:, 0] = x0
         Ad = np.eye(13) + DT * srbd_qp.continuous_A(x0[2])
-        for i in range(10):
+        for i in range(N):
             X[:, i + 1] = Ad @ X[:, i] + DT * srbd_qp.continuous_B(x0[2], r[i]) @ out["U"][b][i]
-        assert close(out["X"][b].T, X, atol=2e-5, rtol=1e-4)
-    perm = rng.permutation(4096)
+        assert close(out["X"][b].T, X, atol=2e-5 * (N / 10) ** 2, rtol=1e-4)
+    perm = rng.permutation(B)
     pb2 = pkg.problems.ProblemBatch(pb.x0[perm], pb.r[perm], pb.stance[perm], pb.x_des[perm],
                                     pb.mu[perm], pb.gait_id[perm], pb.tick[perm])
     out2 = gpu_solve(pb2, warm_mode=0)

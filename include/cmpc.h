@@ -10,7 +10,10 @@
  * Conventions
  *  - All array arguments of the non-`_host` functions are CUDA DEVICE pointers
  *    (e.g. torch `tensor.data_ptr()`), fp32, row-major, contiguous, owned by the caller.
- *  - B problems per call, horizon N fixed per handle.  Legs are FL, FR, HL, HR.
+ *  - B problems per call, horizon N fixed per handle (any 1 <= N <= cmpc_max_horizon(), as the
+ *    reference accepts any params['N'], src/main.py:41; a horizon without its own compiled kernel
+ *    runs on the next compiled one with all-swing, zero-cost padding stages - same optimum).
+ *    Legs are FL, FR, HL, HR.
  *      x0     [B,13]      Theta(3) p(3) omega(3) v(3) g        (src/mpc.py:190-198)
  *      r      [B,N,4,3]   lever arms foot - com per stage/leg    (src/mpc.py:218-239)
  *      mask   [B,N] uint8 bit l = 1  <=> leg l in stance at stage i
@@ -26,6 +29,8 @@
  *    `cmpc_last_error()` returns a thread-local description of the last failure.
  *  - A handle owns the warm-start state (previous primal/dual solution per problem slot,
  *    src/mpc.py:270-271) and scratch; one handle must not be used from two threads at once.
+ *    Disjoint slot ranges [slot0, slot0+B) of one handle may be in flight on different streams.
+ *  - No entry point changes the calling thread's current CUDA device.
  */
 #ifndef CMPC_H
 #define CMPC_H
@@ -80,8 +85,8 @@ typedef struct cmpc_config {
   int32_t adaptive_rho_interval; /* OSQP-style rho adaptation every k iterations, 0 = off */
   float adaptive_rho_tolerance;  /* refactor when rho changes by more than this factor (5) */
   float rho_min, rho_max;        /* clamp of the adapted rho                                 */
-  int32_t kernel_variant; /* 0 = default thread layout; >0 selects an alternative (more threads
-                             per problem) where one is compiled, see DESIGN.md            */
+  int32_t kernel_variant; /* 0 = default thread layout; >0 selects an alternative where one is
+                             compiled (cmpc_has_variant), else the default; see DESIGN.md */
   int32_t lpt_schedule; /* >0: batches of at least this size are launched hardest-first
                            (conditioning score), 0 = launch in batch order               */
   int32_t device;       /* CUDA device ordinal                                       */
@@ -95,8 +100,10 @@ typedef struct cmpc_config {
                            static contact schedules (closed-loop use); 0 = refactorise every call.
                            (One entry per gait phase was tried for steady-state walking: the lever
                            arms of successive gait cycles differ by more than a safe tolerance.)
-                           Costs 4*6N*(6N+20) bytes per slot.  Compiled for N = 10 and N = 30 (default
-                           thread layout; kernel_variant is ignored), other horizons: UNSUPPORTED. */
+                           Costs 4*6N*(6N+20) bytes per slot.  Compiled for the N = 10 and N = 30 kernels
+                           (default thread layout; kernel_variant is ignored; horizons padded onto them
+                           included), other horizons: UNSUPPORTED.  Needs check_every to be a multiple of
+                           refresh_every (the stopping test then runs on a recomputed gradient).      */
   float cache_tol_r, cache_tol_yaw; /* metres / radians (defaults 2e-3, 2e-3)               */
   int32_t cache_max_iter;  /* a solve that needs more iterations drops its cache entry (30) */
   int32_t time_kernel;  /* 1 = bracket every solve-kernel launch of cmpc_solve with CUDA events on the
@@ -138,9 +145,14 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0,
 int cmpc_condense(cmpc_handle* h, int32_t B, const float* x0, const float* r,
                   const uint8_t* mask, const float* x_des, float* H, float* g, void* stream);
 
-/* Warm-start state (src/mpc.py:270-271 `set_initial`): forget it for the slots whose
- * `slot_mask[i] != 0` (all slots if slot_mask == NULL; HOST pointer of max_batch bytes). */
+/* Warm-start state (src/mpc.py:270-271 `set_initial`): forget it (and the cached factorisation)
+ * for the slots whose `slot_mask[i] != 0` (all slots if slot_mask == NULL; HOST pointer of
+ * max_batch bytes).  Host-synchronous: waits for all work in flight on the device first. */
 int cmpc_reset_warm(cmpc_handle* h, const uint8_t* slot_mask);
+/* Stream-ordered form for slots [slot0, slot0+B): `slot_mask` is a DEVICE pointer of B bytes (or
+ * NULL = all of them); enqueued on `stream`, usable inside a CUDA graph capture. */
+int cmpc_reset_warm_async(cmpc_handle* h, int32_t B, int32_t slot0, const uint8_t* slot_mask,
+                          void* stream);
 /* Copy warm-start forces x [B,N,12] and duals y [B,N,4,3] of slots [slot0, slot0+B)
  * to / from DEVICE buffers (y may be NULL). */
 int cmpc_get_warm(cmpc_handle* h, int32_t B, int32_t slot0, float* x, float* y, void* stream);
@@ -218,8 +230,15 @@ int cmpc_last_kernel_ms(cmpc_handle* h, float* ms);
 /* Number of kernels this library has launched on behalf of `h` since creation. */
 int64_t cmpc_launch_count(const cmpc_handle* h);
 
-/* Horizons the compiled kernels cover: writes up to `cap` values, returns the count. */
+/* Horizons with their own compiled kernel: writes up to `cap` values, returns the count. */
 int cmpc_supported_horizons(int32_t* out, int32_t cap);
+/* Largest horizon a handle can be created for; the compiled horizon that horizon N runs on
+ * (N itself, or the next larger compiled one; negative error code outside 1..max). */
+int cmpc_max_horizon(void);
+int cmpc_kernel_horizon(int32_t N);
+/* 1 if thread-layout `variant` (cfg.kernel_variant) is compiled for the kernel horizon of N; the
+ * alternative single-CTA layouts need a build with -DCMPC_EXTRA_LAYOUTS. */
+int cmpc_has_variant(int32_t N, int32_t variant);
 
 int cmpc_version(void);               /* major*1000 + minor */
 const char* cmpc_last_error(void);

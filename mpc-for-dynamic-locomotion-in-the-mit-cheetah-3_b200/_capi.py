@@ -25,7 +25,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 SYMBOLS = ("cmpc_default_config", "cmpc_create", "cmpc_destroy", "cmpc_solve", "cmpc_solve_host",
            "cmpc_condense", "cmpc_reset_warm", "cmpc_get_warm", "cmpc_set_warm",
            "cmpc_launch_count", "cmpc_supported_horizons", "cmpc_version", "cmpc_last_error",
-           "cmpc_assemble", "cmpc_plant_step", "cmpc_fp32_peak", "cmpc_leg_torques", "cmpc_last_kernel_ms", "cmpc_get_cache_meta", "cmpc_accumulate_stats")
+           "cmpc_assemble", "cmpc_plant_step", "cmpc_fp32_peak", "cmpc_leg_torques", "cmpc_last_kernel_ms", "cmpc_get_cache_meta", "cmpc_accumulate_stats",
+           "cmpc_reset_warm_async", "cmpc_max_horizon", "cmpc_kernel_horizon", "cmpc_has_variant")
 
 
 class CmpcError(RuntimeError):
@@ -101,6 +102,10 @@ def lib() -> C.CDLL:
                                   f32p, f32p, i32p]
     L.cmpc_condense.argtypes = [vp, i32, f32p, f32p, u8p, f32p, f32p, f32p, vp]
     L.cmpc_reset_warm.argtypes = [vp, u8p]
+    L.cmpc_reset_warm_async.argtypes = [vp, i32, i32, u8p, vp]
+    L.cmpc_max_horizon.argtypes = []
+    L.cmpc_kernel_horizon.argtypes = [i32]
+    L.cmpc_has_variant.argtypes = [i32, i32]
     L.cmpc_get_warm.argtypes = [vp, i32, i32, f32p, f32p, vp]
     L.cmpc_set_warm.argtypes = [vp, i32, i32, f32p, f32p, vp]
     gtp = C.POINTER(GaitTables)
@@ -139,6 +144,18 @@ def fp32_peak(device=0) -> float:
     v = C.c_float()
     check(lib().cmpc_fp32_peak(device, C.byref(v)))
     return float(v.value)
+
+
+def kernel_horizon(N: int) -> int:
+    """Compiled horizon that horizon N runs on (raises CmpcError outside 1..cmpc_max_horizon())."""
+    rc = lib().cmpc_kernel_horizon(int(N))
+    if rc < 0:
+        check(rc)
+    return rc
+
+
+def has_variant(N: int, variant: int) -> bool:
+    return bool(lib().cmpc_has_variant(int(N), int(variant)))
 
 
 def supported_horizons():

@@ -54,6 +54,24 @@ void axis_gram(int N, double dt, const float* w, std::vector<double>& M) {
   }
 }
 
+// Makes `dev` current for the lifetime of the guard and restores the caller's device afterwards
+// (a handle on device k must not change the calling thread's current device, which is torch's too).
+struct DeviceGuard {
+  int prev = -1, dev;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int d) : dev(d) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
+#define DEVICE_GUARD(h)                                                                   \
+  DeviceGuard guard_((h)->cfg.device);                                                    \
+  if (guard_.err != cudaSuccess)                                                          \
+    return fail(CMPC_ERR_CUDA, "cudaSetDevice(%d) failed: %s", (h)->cfg.device, cudaGetErrorString(guard_.err))
+
 struct Staging {
   char* h_in = nullptr;    // pinned
   char* h_out = nullptr;   // pinned
@@ -68,6 +86,13 @@ struct Staging {
 
 struct cmpc_handle {
   cmpc_config cfg;
+  int NK = 0;                       // horizon of the solve kernel (cfg.N, or the next compiled one)
+  float* d_pad_r = nullptr;         // NK-layout scratch of a padded horizon (NK != cfg.N)
+  uint8_t* d_pad_mask = nullptr;
+  float* d_pad_xdes = nullptr;
+  float* d_pad_U = nullptr;
+  float* d_pad_X = nullptr;
+  int hist_slots = 0;
   float* d_Minv = nullptr;
   float* d_Mg = nullptr;
   float* d_warm_x = nullptr;
@@ -92,7 +117,6 @@ namespace {
 using SolveLaunch = cudaError_t (*)(const cmpc::SolveParams&, cudaStream_t);
 using CondenseLaunch = cudaError_t (*)(const cmpc::CondenseParams&, cudaStream_t);
 using ScoreLaunch = cudaError_t (*)(const cmpc::ScoreParams&, cudaStream_t);
-using AssembleLaunch = cudaError_t (*)(const cmpc::AssembleParams&, cudaStream_t);
 
 template <int N, int SPLIT, int MINB, int R = 1, bool CACHE = false>
 cudaError_t launch_solve(const cmpc::SolveParams& p, cudaStream_t s) {
@@ -117,12 +141,6 @@ cudaError_t launch_solve_cluster(const cmpc::SolveParams& p, cudaStream_t s) {
   return cudaLaunchKernelEx(&cfg, cmpc::solve_cluster_kernel<NL, CL, SPLIT, MINB>, p);
 }
 template <int N>
-cudaError_t launch_assemble(const cmpc::AssembleParams& p, cudaStream_t s) {
-  const int total = p.B * (N + 1);
-  cmpc::assemble_kernel<N><<<(total + 127) / 128, 128, 0, s>>>(p);
-  return cudaGetLastError();
-}
-template <int N>
 cudaError_t launch_score(const cmpc::ScoreParams& p, cudaStream_t s) {
   cmpc::score_kernel<N><<<(p.B + 127) / 128, 128, 0, s>>>(p);
   return cudaGetLastError();
@@ -133,43 +151,64 @@ cudaError_t launch_condense(const cmpc::CondenseParams& p, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+constexpr int kVariants = 5;
 struct HorizonEntry {
   int N;
-  SolveLaunch solve[5];      // thread-layout variants (nullptr = not compiled)
+  SolveLaunch solve[kVariants];   // thread-layout variants (nullptr = not compiled)
   CondenseLaunch condense;
   ScoreLaunch score;
-  AssembleLaunch assemble;
-  SolveLaunch solve_cached;  // default layout with the factorisation cache compiled in, or nullptr
+  SolveLaunch solve_cached;       // default layout with the factorisation cache compiled in, or nullptr
 };
 
 // Horizons with compiled kernels.  <N, SPLIT, MINB, R>: a thread owns an R x (6N/SPLIT) register
 // tile of the 6N x 6N wrench matrix (R rows, one of SPLIT column slices), <= 96 floats.
-// Slot 0 is the default layout, the others are alternatives selectable with kernel_variant
-// (measured on B200: N=10 <10,1,8> 12.1 M solves/s vs 9.5-10.7 M for the R-blocked layouts;
-// N=30 <30,6,1,3> 764 k solves/s vs 703 k for <30,3,1>).
+// Slot 0 is the default layout; slot 2 of N = 20 / 30 is the thread-block-cluster kernel on the same
+// horizon (tests compare the two layouts on the same problems).  The other slots hold alternative
+// single-CTA layouts that were measured SLOWER on B200 (N=10: 8.4-10.7 vs 12.4 M solves/s; N=30:
+// 703 k vs 764 k) and are only compiled with -DCMPC_EXTRA_LAYOUTS (cmpc_has_variant tells).
+// Any other horizon N <= 60 runs padded on the next compiled one (see pad_kernel).
+#ifdef CMPC_EXTRA_LAYOUTS
+#define CMPC_X(...) __VA_ARGS__
+#else
+#define CMPC_X(...) nullptr
+#endif
 const HorizonEntry kHorizons[] = {
-    {4, {launch_solve<4, 1, 8>, nullptr, nullptr}, launch_condense<4>, launch_score<4>, launch_assemble<4>},
-    {5, {launch_solve<5, 1, 8>, nullptr, nullptr}, launch_condense<5>, launch_score<5>, launch_assemble<5>},
-    {8, {launch_solve<8, 1, 8>, nullptr, nullptr}, launch_condense<8>, launch_score<8>, launch_assemble<8>},
-    {10, {launch_solve<10, 1, 8>, launch_solve<10, 2, 4>, launch_solve<10, 4, 2>, launch_solve<10, 2, 8, 2>, launch_solve<10, 5, 8, 5>}, launch_condense<10>, launch_score<10>, launch_assemble<10>, launch_solve<10, 1, 8, 1, true>},
-    {12, {launch_solve<12, 2, 4>, nullptr, nullptr}, launch_condense<12>, launch_score<12>, launch_assemble<12>},
-    {16, {launch_solve<16, 2, 3>, nullptr, nullptr}, launch_condense<16>, launch_score<16>, launch_assemble<16>},
-    {20, {launch_solve<20, 2, 2>, launch_solve<20, 3, 1>, launch_solve_cluster<10, 2, 2, 3>}, launch_condense<20>, launch_score<20>, launch_assemble<20>},
-    {30, {launch_solve<30, 6, 1, 3>, launch_solve<30, 3, 1>, launch_solve_cluster<10, 3, 3, 2>, launch_solve<30, 6, 1, 2>, launch_solve<30, 3, 1, 2>}, launch_condense<30>, launch_score<30>, launch_assemble<30>, launch_solve<30, 6, 1, 3, true>},
-    {40, {launch_solve_cluster<10, 4, 4, 1>, nullptr, nullptr}, nullptr, launch_score<40>, launch_assemble<40>},
-    {60, {launch_solve_cluster<10, 6, 6, 1>, nullptr, nullptr}, nullptr, launch_score<60>, launch_assemble<60>},
+    {4, {launch_solve<4, 1, 8>}, launch_condense<4>, launch_score<4>, nullptr},
+    {5, {launch_solve<5, 1, 8>}, launch_condense<5>, launch_score<5>, nullptr},
+    {8, {launch_solve<8, 1, 8>}, launch_condense<8>, launch_score<8>, nullptr},
+    {10, {launch_solve<10, 1, 8>, CMPC_X(launch_solve<10, 2, 4>), CMPC_X(launch_solve<10, 4, 2>),
+          CMPC_X(launch_solve<10, 2, 8, 2>), CMPC_X(launch_solve<10, 5, 8, 5>)},
+     launch_condense<10>, launch_score<10>, launch_solve<10, 1, 8, 1, true>},
+    {12, {launch_solve<12, 2, 4>}, launch_condense<12>, launch_score<12>, nullptr},
+    {16, {launch_solve<16, 2, 3>}, launch_condense<16>, launch_score<16>, nullptr},
+    {20, {launch_solve<20, 2, 2>, CMPC_X(launch_solve<20, 3, 1>), launch_solve_cluster<10, 2, 2, 3>},
+     launch_condense<20>, launch_score<20>, nullptr},
+    {30, {launch_solve<30, 6, 1, 3>, CMPC_X(launch_solve<30, 3, 1>), launch_solve_cluster<10, 3, 3, 2>,
+          CMPC_X(launch_solve<30, 6, 1, 2>), CMPC_X(launch_solve<30, 3, 1, 2>)},
+     launch_condense<30>, launch_score<30>, launch_solve<30, 6, 1, 3, true>},
+    {40, {launch_solve_cluster<10, 4, 4, 1>}, nullptr, launch_score<40>, nullptr},
+    {60, {launch_solve_cluster<10, 6, 6, 1>}, nullptr, launch_score<60>, nullptr},
 };
+constexpr int kMaxHorizon = 60;
 
 const HorizonEntry* find_horizon(int N) {
   for (const auto& e : kHorizons)
     if (e.N == N) return &e;
   return nullptr;
 }
+// the compiled horizon a user horizon runs on: itself, or the next larger one (padded)
+const HorizonEntry* kernel_horizon(int N) {
+  if (N < 1) return nullptr;
+  for (const auto& e : kHorizons)
+    if (e.N >= N) return &e;
+  return nullptr;
+}
 
-SolveLaunch pick_solve(const cmpc_config& c) {
-  const HorizonEntry* e = find_horizon(c.N);
+SolveLaunch pick_solve(const cmpc_handle* h) {
+  const cmpc_config& c = h->cfg;
+  const HorizonEntry* e = find_horizon(h->NK);
   if (c.cache_factorization && e->solve_cached) return e->solve_cached;
-  const int v = (c.kernel_variant >= 0 && c.kernel_variant < 5) ? c.kernel_variant : 0;
+  const int v = (c.kernel_variant >= 0 && c.kernel_variant < kVariants) ? c.kernel_variant : 0;
   return e->solve[v] ? e->solve[v] : e->solve[0];
 }
 
@@ -208,29 +247,95 @@ void fill_solve_params(const cmpc_handle* h, cmpc::SolveParams& p) {
   p.cache_tol_yaw = c.cache_tol_yaw;
   p.cache_max_iter = c.cache_max_iter;
   p.cache_hit = h->d_cache_hit;
+  p.n_eff = c.N;                       // < NK on a padded horizon
 }
 
-// Enqueue the LPT ordering of a batch (2 small kernels) and point p.order at it.
-// `order_off` lets the host path order several chunks independently.
-int schedule_batch(cmpc_handle* h, cmpc::SolveParams& p, int order_off, int hist_slot, cudaStream_t s) {
+// Enqueue the LPT ordering of a batch (2 small kernels) and point p.order at it.  The scratch
+// (score, order, histogram) is carved out by the batch's slot range, so that disjoint slot ranges
+// of one handle may be solved concurrently on different streams: order/score live at
+// [slot0, slot0 + B), the histogram at slot0 / lpt_schedule (two disjoint ranges of >= lpt_schedule
+// slots each cannot share that quotient).
+int schedule_batch(cmpc_handle* h, cmpc::SolveParams& p, cudaStream_t s) {
   p.order = nullptr;
   if (!h->cfg.lpt_schedule || p.B < h->cfg.lpt_schedule) return CMPC_OK;
   if ((reinterpret_cast<uintptr_t>(p.r) & 15u) != 0) return CMPC_OK;   // score_kernel reads r with 16-byte loads
   const cmpc_config& c = h->cfg;
+  const int hist_slot = p.slot0 / c.lpt_schedule;
+  if (hist_slot >= h->hist_slots) return CMPC_OK;
   cmpc::ScoreParams sp{};
   sp.x0 = p.x0; sp.r = p.r; sp.mask = p.mask; sp.Mg = h->d_Mg;
-  sp.score = h->d_score + order_off;
+  sp.score = h->d_score + p.slot0;
   sp.hist = h->d_hist + 64 * hist_slot;
   sp.B = p.B;
   sp.inv_mass = 1.0f / c.mass;
   for (int i = 0; i < 3; ++i) sp.ib[i] = c.ibody_inv[i];
   // (one fused single-CTA score+sort kernel was measured slower than these two launches:
   // its dependent load rounds cost more than the kernel boundary it saves)
-  CUDA_TRY(find_horizon(c.N)->score(sp, s));
-  cmpc::order_kernel<<<1, 1024, 0, s>>>(sp.score, sp.hist, h->d_order + order_off, p.B);
+  CUDA_TRY(find_horizon(h->NK)->score(sp, s));
+  cmpc::order_kernel<<<1, 1024, 0, s>>>(sp.score, sp.hist, h->d_order + p.slot0, p.B);
   CUDA_TRY(cudaGetLastError());
   h->launches.fetch_add(2);
-  p.order = h->d_order + order_off;
+  p.order = h->d_order + p.slot0;
+  return CMPC_OK;
+}
+
+// pad -> schedule -> solve -> unpad of one batch on one stream; all pointers are device-visible
+// (device memory, or page-locked host memory mapped into the device's address space)
+int solve_device(cmpc_handle* h, int B, int slot0, const float* x0, const float* r, const uint8_t* mask,
+                 const float* x_des, const float* mu, float* U, float* X, int32_t* iters, float* pri_res,
+                 float* dua_res, int32_t* status, cudaStream_t s, bool timed) {
+  const int N = h->cfg.N, NK = h->NK;
+  cmpc::SolveParams p{};
+  fill_solve_params(h, p);
+  p.x0 = x0; p.mu = mu; p.iters = iters; p.pri_res = pri_res; p.dua_res = dua_res; p.status = status;
+  p.B = B;
+  p.slot0 = slot0;
+  if (NK == N) {
+    p.r = r; p.mask = mask; p.x_des = x_des; p.U = U; p.X = X;
+  } else {
+    cmpc::PadParams pp{};
+    pp.r = r; pp.mask = mask; pp.x_des = x_des;
+    pp.r_k = h->d_pad_r + (size_t)slot0 * 12 * NK;
+    pp.mask_k = h->d_pad_mask + (size_t)slot0 * NK;
+    pp.x_des_k = h->d_pad_xdes + (size_t)slot0 * 13 * (NK + 1);
+    pp.B = B; pp.N = N; pp.NK = NK;
+    const long long items = (long long)B * (12 * NK + 13 * (NK + 1) + NK);
+    cmpc::pad_kernel<<<(unsigned)((items + 255) / 256), 256, 0, s>>>(pp);
+    CUDA_TRY(cudaGetLastError());
+    h->launches.fetch_add(1);
+    p.r = pp.r_k; p.mask = pp.mask_k; p.x_des = pp.x_des_k;
+    p.U = h->d_pad_U + (size_t)slot0 * 12 * NK;
+    p.X = X ? h->d_pad_X + (size_t)slot0 * 13 * (NK + 1) : nullptr;
+  }
+  int rc = schedule_batch(h, p, s);
+  if (rc) return rc;
+  static const bool dbg = std::getenv("CMPC_DEBUG_CLOCKS") != nullptr;   // developer aid, synchronous
+  if (dbg) CUDA_TRY(cudaMalloc(&p.dbg_clk, 8 * sizeof(long long)));
+  if (timed) {
+    if (!h->ev0) { CUDA_TRY(cudaEventCreate(&h->ev0)); CUDA_TRY(cudaEventCreate(&h->ev1)); }
+    CUDA_TRY(cudaEventRecord(h->ev0, s));
+  }
+  CUDA_TRY(pick_solve(h)(p, s));
+  if (timed) {
+    CUDA_TRY(cudaEventRecord(h->ev1, s));
+    h->timed = true;
+  }
+  h->launches.fetch_add(1);
+  if (dbg) {
+    long long c[8];
+    CUDA_TRY(cudaMemcpy(c, p.dbg_clk, sizeof c, cudaMemcpyDeviceToHost));
+    cudaFree(p.dbg_clk);
+    std::fprintf(stderr, "cmpc clocks (CTA 0): load %lld geometry %lld P-build %lld sweep %lld init %lld admm %lld output %lld\n",
+                 c[1] - c[0], c[2] - c[1], c[3] - c[2], c[4] - c[3], c[5] - c[4], c[6] - c[5], c[7] - c[6]);
+  }
+  if (NK != N) {
+    cmpc::UnpadParams up{};
+    up.U_k = p.U; up.X_k = p.X; up.U = U; up.X = X; up.B = B; up.N = N; up.NK = NK;
+    const long long items = (long long)B * (12 * N + (X ? 13 * (N + 1) : 0));
+    cmpc::unpad_kernel<<<(unsigned)((items + 255) / 256), 256, 0, s>>>(up);
+    CUDA_TRY(cudaGetLastError());
+    h->launches.fetch_add(1);
+  }
   return CMPC_OK;
 }
 
@@ -257,6 +362,19 @@ int cmpc_supported_horizons(int32_t* out, int32_t cap) {
     ++n;
   }
   return n;
+}
+
+int cmpc_max_horizon(void) { return kMaxHorizon; }
+
+int cmpc_kernel_horizon(int32_t N) {
+  const HorizonEntry* e = kernel_horizon(N);
+  return e ? e->N : fail(CMPC_ERR_UNSUPPORTED, "horizon N=%d is outside 1..%d", N, kMaxHorizon);
+}
+
+int cmpc_has_variant(int32_t N, int32_t variant) {
+  const HorizonEntry* e = kernel_horizon(N);
+  if (!e || variant < 0 || variant >= kVariants) return 0;
+  return e->solve[variant] != nullptr ? 1 : 0;
 }
 
 int cmpc_default_config(cmpc_config* cfg, int32_t N, int32_t max_batch) {
@@ -304,8 +422,9 @@ int cmpc_create(const cmpc_config* cfg, cmpc_handle** out) {
   if (!cfg || !out) return fail(CMPC_ERR_INVALID, "null argument");
   *out = nullptr;
   const cmpc_config& c = *cfg;
-  if (!find_horizon(c.N))
-    return fail(CMPC_ERR_UNSUPPORTED, "horizon N=%d has no compiled kernel (see cmpc_supported_horizons)", c.N);
+  const HorizonEntry* he = kernel_horizon(c.N);
+  if (!he)
+    return fail(CMPC_ERR_UNSUPPORTED, "horizon N=%d is outside 1..%d (largest compiled kernel)", c.N, kMaxHorizon);
   if (c.max_batch <= 0) return fail(CMPC_ERR_INVALID, "max_batch must be positive");
   if (!(c.dt > 0) || !(c.mass > 0) || !(c.rho > 0) || !(c.sigma >= 0) || !(c.alpha > 0 && c.alpha < 2))
     return fail(CMPC_ERR_INVALID, "dt, mass, rho must be > 0, sigma >= 0, 0 < alpha < 2");
@@ -315,6 +434,10 @@ int cmpc_create(const cmpc_config* cfg, cmpc_handle** out) {
   if (c.warm_mode < 0 || c.warm_mode > 2) return fail(CMPC_ERR_INVALID, "bad warm_mode");
   if (c.cache_factorization && (!(c.cache_tol_r >= 0.f) || !(c.cache_tol_yaw >= 0.f) || c.cache_max_iter < 0))
     return fail(CMPC_ERR_INVALID, "cache tolerances and cache_max_iter must be >= 0");
+  if (c.cache_factorization && c.refresh_every > 0 && c.check_every % c.refresh_every != 0)
+    return fail(CMPC_ERR_INVALID, "with cache_factorization the termination test must run on a freshly "
+                                  "recomputed gradient: check_every must be a multiple of refresh_every");
+  if (c.lpt_schedule < 0) return fail(CMPC_ERR_INVALID, "lpt_schedule must be >= 0");
   if (c.adaptive_rho_interval < 0 || (c.adaptive_rho_interval > 0 && !(c.adaptive_rho_tolerance > 1.f)))
     return fail(CMPC_ERR_INVALID, "adaptive_rho_interval >= 0 and adaptive_rho_tolerance > 1 required");
   if (!(c.rho_min > 0.f) || !(c.rho_min <= c.rho_max)) return fail(CMPC_ERR_INVALID, "0 < rho_min <= rho_max required");
@@ -329,44 +452,58 @@ int cmpc_create(const cmpc_config* cfg, cmpc_handle** out) {
     return fail(CMPC_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
   }
   if (c.device < 0 || c.device >= ndev) return fail(CMPC_ERR_INVALID, "device %d of %d", c.device, ndev);
-  CUDA_TRY(cudaSetDevice(c.device));
+  DeviceGuard guard_(c.device);
+  if (guard_.err != cudaSuccess)
+    return fail(CMPC_ERR_CUDA, "cudaSetDevice(%d) failed: %s", c.device, cudaGetErrorString(guard_.err));
 
-  const int N = c.N;
-  std::vector<double> M, Mi;
-  axis_gram(N, (double)c.dt, c.w, M);
-  Mi = M;
+  const int Nu = c.N, N = he->N;       // user horizon, kernel horizon (N > Nu: padded, see pad_kernel)
+  std::vector<double> Mu, Miu;
+  axis_gram(Nu, (double)c.dt, c.w, Mu);
+  Miu = Mu;
   for (int a = 0; a < 6; ++a) {
     // plain Gauss-Jordan with the textbook sign handling
-    double* A = Mi.data() + (size_t)a * N * N;
-    std::vector<double> aug((size_t)N * 2 * N, 0.0);
-    for (int i = 0; i < N; ++i) {
-      for (int j = 0; j < N; ++j) aug[(size_t)i * 2 * N + j] = A[i * N + j];
-      aug[(size_t)i * 2 * N + N + i] = 1.0;
+    double* A = Miu.data() + (size_t)a * Nu * Nu;
+    std::vector<double> aug((size_t)Nu * 2 * Nu, 0.0);
+    for (int i = 0; i < Nu; ++i) {
+      for (int j = 0; j < Nu; ++j) aug[(size_t)i * 2 * Nu + j] = A[i * Nu + j];
+      aug[(size_t)i * 2 * Nu + Nu + i] = 1.0;
     }
-    for (int k = 0; k < N; ++k) {
-      const double piv = aug[(size_t)k * 2 * N + k];
+    for (int k = 0; k < Nu; ++k) {
+      const double piv = aug[(size_t)k * 2 * Nu + k];
       if (!(piv > 0.0) || !std::isfinite(piv))
         return fail(CMPC_ERR_INVALID, "horizon Gram matrix of axis %d is not positive definite "
                                       "(position and velocity weight both zero?)", a);
-      for (int j = 0; j < 2 * N; ++j) aug[(size_t)k * 2 * N + j] /= piv;
-      for (int i = 0; i < N; ++i) {
+      for (int j = 0; j < 2 * Nu; ++j) aug[(size_t)k * 2 * Nu + j] /= piv;
+      for (int i = 0; i < Nu; ++i) {
         if (i == k) continue;
-        const double f = aug[(size_t)i * 2 * N + k];
+        const double f = aug[(size_t)i * 2 * Nu + k];
         if (f == 0.0) continue;
-        for (int j = 0; j < 2 * N; ++j) aug[(size_t)i * 2 * N + j] -= f * aug[(size_t)k * 2 * N + j];
+        for (int j = 0; j < 2 * Nu; ++j) aug[(size_t)i * 2 * Nu + j] -= f * aug[(size_t)k * 2 * Nu + j];
       }
     }
+    for (int i = 0; i < Nu; ++i)
+      for (int j = 0; j < Nu; ++j) A[i * Nu + j] = aug[(size_t)i * 2 * Nu + Nu + j];
+  }
+  // embed into the kernel horizon: blockdiag(M_Nu, I) per axis (the tail stages are all-swing, their
+  // wrench rows decouple; any positive definite filler works)
+  std::vector<float> Mf((size_t)6 * N * N, 0.f), Mif((size_t)6 * N * N, 0.f);
+  for (int a = 0; a < 6; ++a)
     for (int i = 0; i < N; ++i)
-      for (int j = 0; j < N; ++j) A[i * N + j] = aug[(size_t)i * 2 * N + N + j];
-  }
-  std::vector<float> Mf(M.size()), Mif(Mi.size());
-  for (size_t i = 0; i < M.size(); ++i) {
-    Mf[i] = (float)M[i];
-    Mif[i] = (float)Mi[i];
-  }
+      for (int j = 0; j < N; ++j) {
+        const size_t o = ((size_t)a * N + i) * N + j;
+        if (i < Nu && j < Nu) {
+          Mf[o] = (float)Mu[((size_t)a * Nu + i) * Nu + j];
+          Mif[o] = (float)Miu[((size_t)a * Nu + i) * Nu + j];
+        } else if (i == j) {
+          Mf[o] = 1.f;
+          Mif[o] = 1.f;
+        }
+      }
 
   cmpc_handle* h = new cmpc_handle();
   h->cfg = c;
+  h->NK = N;
+  h->hist_slots = c.lpt_schedule > 0 ? c.max_batch / c.lpt_schedule + 1 : 1;
   const size_t mbytes = sizeof(float) * 6 * N * N;
   const size_t slots = (size_t)c.max_batch;
   cudaError_t e;
@@ -377,19 +514,29 @@ int cmpc_create(const cmpc_config* cfg, cmpc_handle** out) {
       (e = cudaMalloc(&h->d_warm_valid, slots)) != cudaSuccess ||
       (e = cudaMalloc(&h->d_score, slots * sizeof(float))) != cudaSuccess ||
       (e = cudaMalloc(&h->d_order, slots * sizeof(int32_t))) != cudaSuccess ||
-      (e = cudaMalloc(&h->d_hist, 4 * 64 * sizeof(int32_t))) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_hist, (size_t)h->hist_slots * 64 * sizeof(int32_t))) != cudaSuccess ||
       (e = cudaMemcpy(h->d_Minv, Mif.data(), mbytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemcpy(h->d_Mg, Mf.data(), mbytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemset(h->d_warm_x, 0, slots * 12 * N * sizeof(float))) != cudaSuccess ||
       (e = cudaMemset(h->d_warm_y, 0, slots * 12 * N * sizeof(float))) != cudaSuccess ||
       (e = cudaMemset(h->d_warm_valid, 0, slots)) != cudaSuccess ||
-      (e = cudaMemset(h->d_hist, 0, 4 * 64 * sizeof(int32_t))) != cudaSuccess) {
+      (e = cudaMemset(h->d_hist, 0, (size_t)h->hist_slots * 64 * sizeof(int32_t))) != cudaSuccess) {
     cmpc_destroy(h);
     return fail(CMPC_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
   }
   if (c.cache_factorization && !find_horizon(N)->solve_cached) {
     cmpc_destroy(h);
-    return fail(CMPC_ERR_UNSUPPORTED, "cache_factorization is compiled for N = 10 and N = 30 only");
+    return fail(CMPC_ERR_UNSUPPORTED, "cache_factorization is compiled for the N = 10 and N = 30 kernels only");
+  }
+  if (N != Nu) {
+    if ((e = cudaMalloc(&h->d_pad_r, slots * 12 * N * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_pad_mask, slots * N)) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_pad_xdes, slots * 13 * (N + 1) * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_pad_U, slots * 12 * N * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_pad_X, slots * 13 * (N + 1) * sizeof(float))) != cudaSuccess) {
+      cmpc_destroy(h);
+      return fail(CMPC_ERR_CUDA, "padded-horizon scratch allocation failed: %s", cudaGetErrorString(e));
+    }
   }
   if (c.cache_factorization) {
     // a tile row is padded to a multiple of 4 SPLIT floats, SPLIT <= 6 in the compiled layouts
@@ -412,7 +559,12 @@ int cmpc_create(const cmpc_config* cfg, cmpc_handle** out) {
 
 int cmpc_destroy(cmpc_handle* h) {
   if (!h) return CMPC_OK;
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard_(h->cfg.device);
+  cudaFree(h->d_pad_r);
+  cudaFree(h->d_pad_mask);
+  cudaFree(h->d_pad_xdes);
+  cudaFree(h->d_pad_U);
+  cudaFree(h->d_pad_X);
   cudaFree(h->d_Minv);
   cudaFree(h->d_Mg);
   cudaFree(h->d_warm_x);
@@ -446,7 +598,7 @@ int cmpc_accumulate_stats(cmpc_handle* h, int32_t B, int32_t slot0, const int32_
   if (rc) return rc;
   if (B == 0) return CMPC_OK;
   if (!iters || !status || !acc) return fail(CMPC_ERR_INVALID, "null pointer");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h);
   cmpc::stats_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
       iters, status, h->d_cache_hit ? h->d_cache_hit + slot0 : nullptr, B,
       reinterpret_cast<unsigned long long*>(acc));
@@ -460,7 +612,7 @@ int cmpc_get_cache_meta(cmpc_handle* h, int32_t B, int32_t slot0, float* meta, v
   if (rc) return rc;
   if (!meta) return fail(CMPC_ERR_INVALID, "null pointer");
   if (!h->d_cache_meta) return fail(CMPC_ERR_INVALID, "the handle was created without cache_factorization");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h);
   CUDA_TRY(cudaMemcpyAsync(meta, h->d_cache_meta + (size_t)slot0 * 4, (size_t)B * 4 * sizeof(float),
                            cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return CMPC_OK;
@@ -481,35 +633,9 @@ int cmpc_solve(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, const 
   if (rc) return rc;
   if (B == 0) return CMPC_OK;
   if (!x0 || !r || !mask || !x_des || !mu || !U) return fail(CMPC_ERR_INVALID, "null input/output pointer");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
-  cmpc::SolveParams p{};
-  fill_solve_params(h, p);
-  p.x0 = x0; p.r = r; p.mask = mask; p.x_des = x_des; p.mu = mu;
-  p.U = U; p.X = X; p.iters = iters; p.pri_res = pri_res; p.dua_res = dua_res; p.status = status;
-  p.B = B;
-  p.slot0 = slot0;
-  rc = schedule_batch(h, p, 0, 0, (cudaStream_t)stream);
-  if (rc) return rc;
-  static const bool dbg = std::getenv("CMPC_DEBUG_CLOCKS") != nullptr;   // developer aid, synchronous
-  if (dbg) CUDA_TRY(cudaMalloc(&p.dbg_clk, 8 * sizeof(long long)));
-  if (h->cfg.time_kernel) {
-    if (!h->ev0) { CUDA_TRY(cudaEventCreate(&h->ev0)); CUDA_TRY(cudaEventCreate(&h->ev1)); }
-    CUDA_TRY(cudaEventRecord(h->ev0, (cudaStream_t)stream));
-  }
-  CUDA_TRY(pick_solve(h->cfg)(p, (cudaStream_t)stream));
-  if (h->cfg.time_kernel) {
-    CUDA_TRY(cudaEventRecord(h->ev1, (cudaStream_t)stream));
-    h->timed = true;
-  }
-  h->launches.fetch_add(1);
-  if (dbg) {
-    long long c[8];
-    CUDA_TRY(cudaMemcpy(c, p.dbg_clk, sizeof c, cudaMemcpyDeviceToHost));
-    cudaFree(p.dbg_clk);
-    std::fprintf(stderr, "cmpc clocks (CTA 0): load %lld geometry %lld P-build %lld sweep %lld init %lld admm %lld output %lld\n",
-                 c[1] - c[0], c[2] - c[1], c[3] - c[2], c[4] - c[3], c[5] - c[4], c[6] - c[5], c[7] - c[6]);
-  }
-  return CMPC_OK;
+  DEVICE_GUARD(h);
+  return solve_device(h, B, slot0, x0, r, mask, x_des, mu, U, X, iters, pri_res, dua_res, status,
+                      (cudaStream_t)stream, h->cfg.time_kernel != 0);
 }
 
 int cmpc_condense(cmpc_handle* h, int32_t B, const float* x0, const float* r, const uint8_t* mask,
@@ -518,7 +644,7 @@ int cmpc_condense(cmpc_handle* h, int32_t B, const float* x0, const float* r, co
   if (B < 0) return fail(CMPC_ERR_INVALID, "negative batch");
   if (B == 0) return CMPC_OK;
   if (!x0 || !r || !mask || !x_des || !H || !g) return fail(CMPC_ERR_INVALID, "null pointer");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h);
   cmpc::CondenseParams p{};
   const cmpc_config& c = h->cfg;
   p.x0 = x0; p.r = r; p.mask = mask; p.x_des = x_des; p.H = H; p.g = g; p.Mg = h->d_Mg;
@@ -528,8 +654,9 @@ int cmpc_condense(cmpc_handle* h, int32_t B, const float* x0, const float* r, co
   for (int i = 0; i < 3; ++i) p.ib[i] = c.ibody_inv[i];
   for (int i = 0; i < 13; ++i) p.w[i] = c.w[i];
   p.r_weight = c.r_weight;
-  if (!find_horizon(c.N)->condense)
-    return fail(CMPC_ERR_UNSUPPORTED, "cmpc_condense is not compiled for N=%d (dense H export needs N <= 30)", c.N);
+  if (h->NK != c.N || !find_horizon(c.N)->condense)
+    return fail(CMPC_ERR_UNSUPPORTED, "cmpc_condense (dense H export, inspection path) is compiled for "
+                "N in {4,5,8,10,12,16,20,30} only, not N=%d", c.N);
   CUDA_TRY(find_horizon(c.N)->condense(p, (cudaStream_t)stream));
   h->launches.fetch_add(1);
   return CMPC_OK;
@@ -560,12 +687,16 @@ int cmpc_assemble(cmpc_handle* h, int32_t B, const cmpc_gait_tables* gt, const i
   if (B == 0) return CMPC_OK;
   if (!tick || !x || !yaw_start || !com_start || !x_des || !r || !mask)
     return fail(CMPC_ERR_INVALID, "null pointer");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h);
   cmpc::AssembleParams p{};
   fill_gait(h, gt, p.gt);
   p.tick = tick; p.x = x; p.yaw_start = yaw_start; p.com_start = com_start;
-  p.x_des = x_des; p.r = r; p.mask = mask; p.B = B;
-  CUDA_TRY(find_horizon(h->cfg.N)->assemble(p, (cudaStream_t)stream));
+  p.x_des = x_des; p.r = r; p.mask = mask; p.B = B; p.N = h->cfg.N;
+  {
+    const long long total = (long long)B * (p.N + 1);
+    cmpc::assemble_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+  }
   h->launches.fetch_add(1);
   return CMPC_OK;
 }
@@ -579,7 +710,7 @@ int cmpc_plant_step(cmpc_handle* h, int32_t B, const cmpc_gait_tables* gt, int32
   if (rc) return rc;
   if (!tick || ((!x || !r || !U || !x_des || !yaw_start || !com_start || !track_err) && B > 0))
     return fail(CMPC_ERR_INVALID, "null pointer");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h);
   cudaStream_t s = (cudaStream_t)stream;
   if (B > 0) {
     cmpc::PlantParams p{};
@@ -609,7 +740,7 @@ int cmpc_leg_torques(cmpc_handle* h, int32_t B, const cmpc_gait_tables* gt, cons
   if (B == 0) return CMPC_OK;
   if (!tick || !U || !J || !Jdot || !Mleg || !cg || !dq || !foot_pos || !foot_vel || !kp || !kd || !tau)
     return fail(CMPC_ERR_INVALID, "null pointer");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h);
   cmpc::LegParams p{};
   fill_gait(h, gt, p.gt);
   p.tick = tick; p.U = U; p.J = J; p.Jdot = Jdot; p.Mleg = Mleg; p.cg = cg; p.dq = dq;
@@ -709,7 +840,7 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, c
   if (rc) return rc;
   if (B == 0) return CMPC_OK;
   if (!x0 || !r || !mask || !x_des || !mu || !U) return fail(CMPC_ERR_INVALID, "null input/output pointer");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  DEVICE_GUARD(h);
   const int N = h->cfg.N;
   Staging& st = h->st;
   if (h->cfg.host_zero_copy) {
@@ -724,18 +855,10 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, c
                     is_pinned(dua_res, &ddu) && is_pinned(status, &dst);
     if (ok && dx0 && dr && dmask && dxd && dmu && dU) {
       if (!st.streams[0]) CUDA_TRY(cudaStreamCreateWithFlags(&st.streams[0], cudaStreamNonBlocking));
-      cmpc::SolveParams p{};
-      fill_solve_params(h, p);
-      p.x0 = (const float*)dx0; p.r = (const float*)dr; p.mask = (const uint8_t*)dmask;
-      p.x_des = (const float*)dxd; p.mu = (const float*)dmu;
-      p.U = (float*)dU; p.X = (float*)dX; p.iters = (int32_t*)dit; p.pri_res = (float*)dpr;
-      p.dua_res = (float*)ddu; p.status = (int32_t*)dst;
-      p.B = B;
-      p.slot0 = slot0;
-      rc = schedule_batch(h, p, 0, 0, st.streams[0]);
+      rc = solve_device(h, B, slot0, (const float*)dx0, (const float*)dr, (const uint8_t*)dmask,
+                        (const float*)dxd, (const float*)dmu, (float*)dU, (float*)dX, (int32_t*)dit,
+                        (float*)dpr, (float*)ddu, (int32_t*)dst, st.streams[0], false);
       if (rc) return rc;
-      CUDA_TRY(pick_solve(h->cfg)(p, st.streams[0]));
-      h->launches.fetch_add(1);
       CUDA_TRY(cudaStreamSynchronize(st.streams[0]));
       return CMPC_OK;
     }
@@ -769,9 +892,6 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, c
       if (!s) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   }
   const Layout La = make_layout(N, st.cap, true);   // arena strides use the allocated capacity
-  cmpc::SolveParams base{};
-  fill_solve_params(h, base);
-  const SolveLaunch solve_fn = pick_solve(h->cfg);
   const size_t nx = (size_t)13 * (N + 1), nu = (size_t)12 * N;
   for (int ci = 0; ci < nchunk; ++ci) {
     const int lo = ci * C, n = (lo + C <= B ? C : B - lo);
@@ -795,24 +915,12 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, c
       std::memcpy(hin + La.mask, mask + (size_t)lo * N, (size_t)n * N);
       CUDA_TRY(cudaMemcpyAsync(din, hin, La.in_total, cudaMemcpyHostToDevice, s));
     }
-    cmpc::SolveParams p = base;
-    p.x0 = (const float*)(din + La.x0);
-    p.r = (const float*)(din + La.r);
-    p.x_des = (const float*)(din + La.xdes);
-    p.mu = (const float*)(din + La.mu);
-    p.mask = (const uint8_t*)(din + La.mask);
-    p.U = (float*)(dout + La.U);
-    p.X = X ? (float*)(dout + La.X) : nullptr;
-    p.iters = (int32_t*)(dout + La.iters);
-    p.pri_res = (float*)(dout + La.pri);
-    p.dua_res = (float*)(dout + La.dua);
-    p.status = (int32_t*)(dout + La.status);
-    p.B = n;
-    p.slot0 = slot0 + lo;
-    rc = schedule_batch(h, p, lo, ci, s);
+    rc = solve_device(h, n, slot0 + lo, (const float*)(din + La.x0), (const float*)(din + La.r),
+                      (const uint8_t*)(din + La.mask), (const float*)(din + La.xdes),
+                      (const float*)(din + La.mu), (float*)(dout + La.U),
+                      X ? (float*)(dout + La.X) : nullptr, (int32_t*)(dout + La.iters),
+                      (float*)(dout + La.pri), (float*)(dout + La.dua), (int32_t*)(dout + La.status), s, false);
     if (rc) return rc;
-    CUDA_TRY(solve_fn(p, s));
-    h->launches.fetch_add(1);
     if (out_pinned) {
       CUDA_TRY(cudaMemcpyAsync(U + (size_t)lo * nu, dout + La.U, (size_t)n * nu * 4, cudaMemcpyDeviceToHost, s));
       if (X) CUDA_TRY(cudaMemcpyAsync(X + (size_t)lo * nx, dout + La.X, (size_t)n * nx * 4, cudaMemcpyDeviceToHost, s));
@@ -841,34 +949,57 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, c
   return CMPC_OK;
 }
 
-int cmpc_reset_warm(cmpc_handle* h, const uint8_t* slot_mask) {
-  if (!h) return fail(CMPC_ERR_INVALID, "null handle");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
-  const size_t slots = (size_t)h->cfg.max_batch;
-  if (h->d_cache_meta) CUDA_TRY(cudaMemset(h->d_cache_meta, 0, slots * 4 * sizeof(float)));   // cached factors too
-  if (!slot_mask) {
-    CUDA_TRY(cudaMemset(h->d_warm_valid, 0, slots));
-    return CMPC_OK;
-  }
-  std::vector<uint8_t> cur(slots);
-  CUDA_TRY(cudaMemcpy(cur.data(), h->d_warm_valid, slots, cudaMemcpyDeviceToHost));
-  for (size_t i = 0; i < slots; ++i)
-    if (slot_mask[i]) cur[i] = 0;
-  CUDA_TRY(cudaMemcpy(h->d_warm_valid, cur.data(), slots, cudaMemcpyHostToDevice));
+int cmpc_reset_warm_async(cmpc_handle* h, int32_t B, int32_t slot0, const uint8_t* slot_mask, void* stream) {
+  int rc = check_batch(h, B, slot0);
+  if (rc) return rc;
+  if (B == 0) return CMPC_OK;
+  DEVICE_GUARD(h);
+  cmpc::reset_warm_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      h->d_warm_valid, h->d_cache_meta, slot_mask, slot0, B);
+  CUDA_TRY(cudaGetLastError());
+  h->launches.fetch_add(1);
   return CMPC_OK;
 }
 
+int cmpc_reset_warm(cmpc_handle* h, const uint8_t* slot_mask) {
+  if (!h) return fail(CMPC_ERR_INVALID, "null handle");
+  DEVICE_GUARD(h);
+  // host-synchronous form: ordered against EVERY stream of the device (solves may be in flight on
+  // non-blocking streams, which the legacy default stream does not wait for)
+  CUDA_TRY(cudaDeviceSynchronize());
+  const int slots = h->cfg.max_batch;
+  uint8_t* d_mask = nullptr;
+  if (slot_mask) {
+    CUDA_TRY(cudaMalloc(&d_mask, (size_t)slots));
+    cudaError_t e = cudaMemcpy(d_mask, slot_mask, (size_t)slots, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(d_mask);
+      return fail(CMPC_ERR_CUDA, "cudaMemcpy of the slot mask failed: %s", cudaGetErrorString(e));
+    }
+  }
+  cmpc::reset_warm_kernel<<<(slots + 255) / 256, 256>>>(h->d_warm_valid, h->d_cache_meta, d_mask, 0, slots);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaFree(d_mask);
+  if (e != cudaSuccess) return fail(CMPC_ERR_CUDA, "reset_warm failed: %s", cudaGetErrorString(e));
+  h->launches.fetch_add(1);
+  return CMPC_OK;
+}
+
+// the handle keeps warm x / y in the kernel horizon's layout [slots][NK][12]; callers use [B][N][12]
 int cmpc_get_warm(cmpc_handle* h, int32_t B, int32_t slot0, float* x, float* y, void* stream) {
   int rc = check_batch(h, B, slot0);
   if (rc) return rc;
   if (!x) return fail(CMPC_ERR_INVALID, "null pointer");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
-  const size_t N = (size_t)h->cfg.N;
-  CUDA_TRY(cudaMemcpyAsync(x, h->d_warm_x + (size_t)slot0 * 12 * N, (size_t)B * 12 * N * 4,
-                           cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (B == 0) return CMPC_OK;
+  DEVICE_GUARD(h);
+  const size_t wu = (size_t)h->cfg.N * 12 * 4, wk = (size_t)h->NK * 12 * 4;
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemcpy2DAsync(x, wu, h->d_warm_x + (size_t)slot0 * 12 * h->NK, wk, wu, (size_t)B,
+                             cudaMemcpyDeviceToDevice, s));
   if (y)
-    CUDA_TRY(cudaMemcpyAsync(y, h->d_warm_y + (size_t)slot0 * 12 * N, (size_t)B * 12 * N * 4,
-                             cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    CUDA_TRY(cudaMemcpy2DAsync(y, wu, h->d_warm_y + (size_t)slot0 * 12 * h->NK, wk, wu, (size_t)B,
+                               cudaMemcpyDeviceToDevice, s));
   return CMPC_OK;
 }
 
@@ -877,16 +1008,16 @@ int cmpc_set_warm(cmpc_handle* h, int32_t B, int32_t slot0, const float* x, cons
   int rc = check_batch(h, B, slot0);
   if (rc) return rc;
   if (!x) return fail(CMPC_ERR_INVALID, "null pointer");
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
-  const size_t N = (size_t)h->cfg.N;
+  if (B == 0) return CMPC_OK;
+  DEVICE_GUARD(h);
+  const size_t wu = (size_t)h->cfg.N * 12 * 4, wk = (size_t)h->NK * 12 * 4;
   cudaStream_t s = (cudaStream_t)stream;
-  CUDA_TRY(cudaMemcpyAsync(h->d_warm_x + (size_t)slot0 * 12 * N, x, (size_t)B * 12 * N * 4,
-                           cudaMemcpyDeviceToDevice, s));
-  if (y)
-    CUDA_TRY(cudaMemcpyAsync(h->d_warm_y + (size_t)slot0 * 12 * N, y, (size_t)B * 12 * N * 4,
-                             cudaMemcpyDeviceToDevice, s));
-  else
-    CUDA_TRY(cudaMemsetAsync(h->d_warm_y + (size_t)slot0 * 12 * N, 0, (size_t)B * 12 * N * 4, s));
+  float* wx = h->d_warm_x + (size_t)slot0 * 12 * h->NK;
+  float* wy = h->d_warm_y + (size_t)slot0 * 12 * h->NK;
+  if (wk != wu) CUDA_TRY(cudaMemsetAsync(wx, 0, wk * B, s));      // padded stages carry no force
+  CUDA_TRY(cudaMemcpy2DAsync(wx, wk, x, wu, wu, (size_t)B, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaMemsetAsync(wy, 0, wk * B, s));
+  if (y) CUDA_TRY(cudaMemcpy2DAsync(wy, wk, y, wu, wu, (size_t)B, cudaMemcpyDeviceToDevice, s));
   CUDA_TRY(cudaMemsetAsync(h->d_warm_valid + slot0, 1, (size_t)B, s));
   return CMPC_OK;
 }

@@ -148,7 +148,8 @@ solve_cluster_kernel(const SolveParams p) {
   const int gi = g0 + ri;                                // global row
   const int rjl = ri / 6, ra = ri % 6;                   // local stage, axis
   const int rj = j0 + rjl;                               // global stage
-  if (is_row && rs == 0) s_h[ri] = wrench_linear_term<N>(rj, ra, s_x0, s_xd, cs, sn, p.w, p.dt);
+  if (is_row && rs == 0)
+    s_h[ri] = wrench_linear_term<N>(rj, ra, s_x0, s_xd, cs, sn, p.w, p.dt, p.n_eff > 0 ? p.n_eff : N);
   __syncthreads();
 
   int ag = 0;        // all-gather counter: buffer parity of s_s / s_red

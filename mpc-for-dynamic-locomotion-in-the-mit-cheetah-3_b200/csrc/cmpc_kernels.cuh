@@ -48,6 +48,7 @@ struct SolveParams {
   const int32_t* __restrict__ order;  // launch order (hardest first) or nullptr
   int32_t B;
   int32_t slot0;
+  int32_t n_eff;                      // stages that carry cost (<= N; the rest is all-swing padding, 0 = N)
   float dt, inv_mass;
   float ib[3];
   float w[13];
@@ -144,42 +145,48 @@ __device__ __forceinline__ void leg_map(float c, float s, const float ib[3], flo
 
 // Tracking error of the free response at stage k on wrench axis a (position-like and
 // velocity-like part; angular velocity error rotated by Rz):  e = free response - x_des.
+// In double: the inputs are fp32, their differences are exact, and the linear term h below is a
+// sum of N terms of size ~1e3 whose rounding in fp32 (~1e-3 absolute) is NOT harmless - the
+// wrench components with the smallest cost curvature (2 w_pos dt^4 ~ 3e-3 per N^2) move by
+// gradient error / curvature, i.e. by tenths of a newton at N = 60 (measured, scripts/gpu_tight_diag.py).
 __device__ __forceinline__ void stage_error(int k, int a, const float* sx0, const float* sxd, float c,
-                                            float s, float dt, float& e_pos, float& e_vel) {
+                                            float s, float dt, double& e_pos, double& e_vel) {
   const float* xd = sxd + 13 * k;
-  const float kf = (float)k;
+  const double kf = (double)k, dtd = (double)dt, cd = (double)c, sd = (double)s;
   if (a < 3) {
-    const float rw0 = a == 0 ? (c * sx0[6] - s * sx0[7]) : (a == 1 ? (s * sx0[6] + c * sx0[7]) : sx0[8]);
-    const float rwd = a == 0 ? (c * xd[6] - s * xd[7]) : (a == 1 ? (s * xd[6] + c * xd[7]) : xd[8]);
-    e_pos = (sx0[a] - xd[a]) + kf * dt * rw0;      // exact difference first
+    const double w0x = sx0[6], w0y = sx0[7], wdx = xd[6], wdy = xd[7];
+    const double rw0 = a == 0 ? (cd * w0x - sd * w0y) : (a == 1 ? (sd * w0x + cd * w0y) : (double)sx0[8]);
+    const double rwd = a == 0 ? (cd * wdx - sd * wdy) : (a == 1 ? (sd * wdx + cd * wdy) : (double)xd[8]);
+    e_pos = ((double)sx0[a] - (double)xd[a]) + kf * dtd * rw0;
     e_vel = rw0 - rwd;
   } else {
     const int aa = a - 3;
-    float pf = (sx0[3 + aa] - xd[3 + aa]) + kf * dt * sx0[9 + aa];
-    float vf = sx0[9 + aa] - xd[9 + aa];
+    double pf = ((double)sx0[3 + aa] - (double)xd[3 + aa]) + kf * dtd * (double)sx0[9 + aa];
+    double vf = (double)sx0[9 + aa] - (double)xd[9 + aa];
     if (aa == 2) {
-      const float g = sx0[12];
-      pf += 0.5f * kf * (kf - 1.f) * dt * dt * g;
-      vf += kf * dt * g;
+      const double g = sx0[12];
+      pf += 0.5 * kf * (kf - 1.0) * dtd * dtd * g;
+      vf += kf * dtd * g;
     }
     e_pos = pf;
     e_vel = vf;
   }
 }
 
-// Linear term of the wrench-space cost: h[6j+a] = 2 sum_{k>j} (w_pos d^2 (k-1-j) e_pos + w_vel d e_vel)
+// Linear term of the wrench-space cost: h[6j+a] = 2 sum_{k>j} (w_pos d^2 (k-1-j) e_pos + w_vel d e_vel),
+// stages k <= n_eff only (the rest of a padded horizon carries no cost)
 template <int N>
 __device__ __forceinline__ float wrench_linear_term(int j, int a, const float* sx0,
                                                     const float* sxd, float c, float s,
-                                                    const float* w, float dt) {
-  const float wp = w[a], wv = w[6 + a];      // w[0:3] Theta, w[3:6] p, w[6:9] omega, w[9:12] v
-  float acc = 0.f;
-  for (int k = j + 1; k <= N; ++k) {
-    float e_pos, e_vel;
+                                                    const float* w, float dt, int n_eff) {
+  const double wp = w[a], wv = w[6 + a], dtd = dt;      // w[0:3] Theta, w[3:6] p, w[6:9] omega, w[9:12] v
+  double acc = 0.0;
+  for (int k = j + 1; k <= n_eff; ++k) {
+    double e_pos, e_vel;
     stage_error(k, a, sx0, sxd, c, s, dt, e_pos, e_vel);
-    acc += 2.f * (wp * dt * dt * (float)(k - 1 - j) * e_pos + wv * dt * e_vel);
+    acc += 2.0 * (wp * dtd * dtd * (double)(k - 1 - j) * e_pos + wv * dtd * e_vel);
   }
-  return acc;
+  return (float)acc;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -209,6 +216,7 @@ solve_kernel(const SolveParams p) {
   __shared__ __align__(8) float s_dump[2 * THREADS];   // scratch target of lanes that own no wrench pair
   __shared__ float s_gl[3 * NLEG];                      // G' h per leg (read at check iterations only)
   __shared__ float s_pre[2][6 * (N + 1)];              // prefix sums for the X output
+  __shared__ double s_e[2][NW];                         // stage errors of the linear term (fp64)
   __shared__ int s_mask[N];
 
   if ((int)blockIdx.x >= p.B) return;
@@ -298,21 +306,26 @@ solve_kernel(const SolveParams p) {
   const int rs = SPLIT == 1 ? 0 : tid / NWR;         // slice-major layout: column slice,
   const int rp = tid - rs * NWR;                     // first row (rows rp + q NWR, q < R)
   const int rj0 = rp / 6, ra = rp % 6;               // stage of the first row, axis of all R rows
+  const int n_eff = p.n_eff > 0 ? p.n_eff : N;
   {
     // linear term h in two steps: the 6N stage errors once (one (k, a) per thread), then the
-    // suffix sums over k > j - the same terms in the same order as wrench_linear_term()
-    float* e_pos = &s_pre[0][0];          // [N][6], free until the output phase
-    float* e_vel = &s_pre[1][0];
-    for (int i = tid; i < NW; i += THREADS)
-      stage_error(i / 6 + 1, i % 6, s_x0, s_xd, cs, sn, p.dt, e_pos[i], e_vel[i]);
+    // suffix sums over k > j - the same terms in the same order as wrench_linear_term(), in double
+    double* e_pos = &s_e[0][0];           // [N][6]
+    double* e_vel = &s_e[1][0];
+    for (int i = tid; i < NW; i += THREADS) {
+      double ep = 0.0, ev = 0.0;
+      if (i / 6 + 1 <= n_eff) stage_error(i / 6 + 1, i % 6, s_x0, s_xd, cs, sn, p.dt, ep, ev);
+      e_pos[i] = ep;
+      e_vel[i] = ev;
+    }
     __syncthreads();
     for (int i = tid; i < NW; i += THREADS) {
       const int j = i / 6, a = i % 6;
-      const float wp = p.w[a], wv = p.w[6 + a], dt = p.dt;
-      float acc = 0.f;
+      const double wp = p.w[a], wv = p.w[6 + a], dt = p.dt;
+      double acc = 0.0;
       for (int k = j + 1; k <= N; ++k)
-        acc += 2.f * (wp * dt * dt * (float)(k - 1 - j) * e_pos[6 * (k - 1) + a] + wv * dt * e_vel[6 * (k - 1) + a]);
-      s_h[i] = acc;
+        acc += 2.0 * (wp * dt * dt * (double)(k - 1 - j) * e_pos[6 * (k - 1) + a] + wv * dt * e_vel[6 * (k - 1) + a]);
+      s_h[i] = (float)acc;
     }
   }
   __syncthreads();
@@ -341,6 +354,7 @@ solve_kernel(const SolveParams p) {
     }
     return;
   }
+  used_cache = false;   // from here on the factor is a fresh one of the current data
   // ---- phase 2: P = M^-1 + E (R x COLS register tiles) -------------------------------------
   // E_j[ra][a'] = sum_l sum_c Gp[ra][c] d Gp[a'][c],  Gp = [Ghat ; I/m]
   float E[R][6];
@@ -995,7 +1009,7 @@ __global__ void __launch_bounds__(256) condense_kernel(const CondenseParams p) {
     }
   }
   for (int i = tid; i < NW; i += 256)
-    s_h[i] = wrench_linear_term<N>(i / 6, i % 6, s_x0, s_xd, cs, sn, p.w, p.dt);
+    s_h[i] = wrench_linear_term<N>(i / 6, i % 6, s_x0, s_xd, cs, sn, p.w, p.dt, N);
   __syncthreads();
   // g = G' h
   for (int u = tid; u < NU; u += 256) {
@@ -1084,11 +1098,11 @@ struct AssembleParams {
   float* __restrict__ x_des;             // [B,N+1,13]
   float* __restrict__ r;                 // [B,N,4,3]
   uint8_t* __restrict__ mask;            // [B,N]
-  int32_t B;
+  int32_t B, N;                          // any horizon (runtime)
 };
 
-template <int N>
 __global__ void __launch_bounds__(128) assemble_kernel(const AssembleParams p) {
+  const int N = p.N;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= p.B * (N + 1)) return;
   const int b = idx / (N + 1), i = idx % (N + 1);
@@ -1189,6 +1203,75 @@ __global__ void __launch_bounds__(128) plant_kernel(const PlantParams p) {
 }
 
 __global__ void tick_kernel(int32_t* tick) { *tick += 1; }
+
+// ---------------------------------------------------------------------------------------
+// Any horizon (reference src/main.py:41 accepts any params['N']): a horizon N without a compiled
+// solve kernel runs on the next compiled horizon NK > N.  The extra stages are all-swing (no
+// unknowns) and carry no cost (SolveParams::n_eff = N; the horizon Gram matrices are those of N
+// with an identity tail), so the padded problem has exactly the optimum of the N-stage problem.
+// pad_kernel copies a batch of user-layout records [B,N,...] into NK-layout scratch, unpad_kernel
+// copies U / X back.  One thread per float of the wider layout, coalesced on that side.
+// ---------------------------------------------------------------------------------------
+struct PadParams {
+  const float* __restrict__ r;        // [B,N,12]
+  const uint8_t* __restrict__ mask;   // [B,N]
+  const float* __restrict__ x_des;    // [B,N+1,13]
+  float* __restrict__ r_k;            // [B,NK,12]
+  uint8_t* __restrict__ mask_k;       // [B,NK]
+  float* __restrict__ x_des_k;        // [B,NK+1,13]
+  int32_t B, N, NK;
+};
+
+__global__ void __launch_bounds__(256) pad_kernel(const PadParams p) {
+  const int per = 12 * p.NK + 13 * (p.NK + 1) + p.NK;       // work items per problem
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)p.B * per) return;
+  const int b = (int)(gid / per);
+  int i = (int)(gid - (long long)b * per);
+  if (i < 12 * p.NK) {
+    p.r_k[(size_t)b * 12 * p.NK + i] = i < 12 * p.N ? __ldg(p.r + (size_t)b * 12 * p.N + i) : 0.f;
+    return;
+  }
+  i -= 12 * p.NK;
+  if (i < 13 * (p.NK + 1)) {
+    const int k = i / 13, c = i - 13 * k;
+    const int ks = k <= p.N ? k : p.N;                      // hold the last desired state (it has no weight)
+    p.x_des_k[(size_t)b * 13 * (p.NK + 1) + i] = __ldg(p.x_des + ((size_t)b * (p.N + 1) + ks) * 13 + c);
+    return;
+  }
+  i -= 13 * (p.NK + 1);
+  p.mask_k[(size_t)b * p.NK + i] = i < p.N ? __ldg(p.mask + (size_t)b * p.N + i) : (uint8_t)0;
+}
+
+struct UnpadParams {
+  const float* __restrict__ U_k;      // [B,NK,12]
+  const float* __restrict__ X_k;      // [B,NK+1,13] or nullptr
+  float* __restrict__ U;              // [B,N,12]
+  float* __restrict__ X;              // [B,N+1,13] or nullptr
+  int32_t B, N, NK;
+};
+
+__global__ void __launch_bounds__(256) unpad_kernel(const UnpadParams p) {
+  const int nu = 12 * p.N, nx = p.X ? 13 * (p.N + 1) : 0, per = nu + nx;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)p.B * per) return;
+  const int b = (int)(gid / per);
+  const int i = (int)(gid - (long long)b * per);
+  if (i < nu) p.U[(size_t)b * nu + i] = p.U_k[(size_t)b * 12 * p.NK + i];
+  else p.X[(size_t)b * nx + (i - nu)] = p.X_k[(size_t)b * 13 * (p.NK + 1) + (i - nu)];
+}
+
+// forget the warm start (and the cached factorisation) of the slots whose mask byte is set
+__global__ void __launch_bounds__(256) reset_warm_kernel(uint8_t* __restrict__ warm_valid,
+                                                         float* __restrict__ cache_meta,
+                                                         const uint8_t* __restrict__ slot_mask,
+                                                         int32_t slot0, int32_t B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  if (slot_mask && !slot_mask[i]) return;
+  warm_valid[slot0 + i] = 0;
+  if (cache_meta) cache_meta[(size_t)(slot0 + i) * 4 + 2] = 0.f;
+}
 
 // Running totals of a closed-loop rollout in one launch: ADMM iterations, problems whose status
 // is not "solved", factorisation-cache hits (meta may be nullptr).  acc[3], unsigned 64-bit.

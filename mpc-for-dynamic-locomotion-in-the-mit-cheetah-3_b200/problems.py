@@ -50,27 +50,40 @@ class BatchedGaitPlan:
         omega_ref = np.broadcast_to(np.asarray(omega_ref, dtype=float), (B,))
         theta = np.broadcast_to(np.asarray(yaw0, dtype=float), (B,)).copy()
         S = int(total_steps)
-        uni = feet0.mean(axis=1)                          # (B,3)
-        dfl = feet0[:, 0, :2] - feet0[:, 2, :2]           # fl - hl
-        dlat = feet0[:, 3, :2] - feet0[:, 2, :2]          # hr - hl
+        # same arithmetic, in the same order, as reference src/footstep_planner.py:72-177 (and
+        # gait.GaitPlan.from_initial): the 2x2 rotations go through np.matmul like the reference's
+        # `Rm @ v`, so that the plan of every robot agrees with the reference planner to the last bit
+        fl, fr, hl, hr = feet0[:, 0], feet0[:, 1], feet0[:, 2], feet0[:, 3]
+        uni = (hl + hr + fl + fr) / 4.0                   # (B,3)
+        dfl = fl[:, :2] - hl[:, :2]
+        dlat = hr[:, :2] - hl[:, :2]
+
+        def rot(th):
+            c, s = np.cos(th), np.sin(th)
+            return np.stack([np.stack([c, -s], -1), np.stack([s, c], -1)], -2)      # (B,2,2)
+
+        def apply(Rm, v):                                  # per-robot Rm @ v (stacked matmul: same BLAS
+            return np.matmul(Rm, v[:, :, None])[:, :, 0]   # kernel, same bits as the reference's 2x2 `@`)
+
         pos = np.zeros((B, S, 4, 3))
         feet_id = np.ones((B, S, 4), dtype=np.int64)
         support = first_swing.copy()
         period = ss + ds
+        Rm = rot(theta)
         for j in range(S):
             if j >= 1:
                 for i in range(int(period.max())):
-                    live = (i < period).astype(float)
-                    theta = theta + live * omega_ref * dt
-                    c, s = np.cos(theta), np.sin(theta)
-                    uni[:, 0] += live * (c * v_ref[:, 0] - s * v_ref[:, 1]) * dt
-                    uni[:, 1] += live * (s * v_ref[:, 0] + c * v_ref[:, 1]) * dt
-            c, s = np.cos(theta), np.sin(theta)
-            torso = np.stack([c * dfl[:, 0] - s * dfl[:, 1], s * dfl[:, 0] + c * dfl[:, 1]], 1)
-            lat = np.stack([c * dlat[:, 0] - s * dlat[:, 1], s * dlat[:, 0] + c * dlat[:, 1]], 1) / 2
+                    live = i < period
+                    theta = np.where(live, theta + omega_ref * dt, theta)
+                    Rm = np.where(live[:, None, None], rot(theta), Rm)
+                    step = apply(Rm, v_ref[:, :2]) * dt
+                    uni[:, :2] = np.where(live[:, None], uni[:, :2] + step, uni[:, :2])
+            torso = apply(Rm, dfl)
+            lat = apply(Rm, dlat) / 2.0
+            half = torso / 2
+            base = uni[:, None, :2] + _SGN_T[None, :, None] * half[:, None, :]     # u +- t/2 (exact sign flip)
             new = np.empty((B, 4, 3))
-            new[:, :, :2] = (uni[:, None, :2] + _SGN_T[None, :, None] * torso[:, None, :] / 2
-                             + _SGN_L[None, :, None] * lat[:, None, :])
+            new[:, :, :2] = base + _SGN_L[None, :, None] * lat[:, None, :]          # (u +- t/2) +- lat
             new[:, :, 2] = uni[:, None, 2]
             if j >= 1:
                 keep = support.astype(bool)[:, :, None]

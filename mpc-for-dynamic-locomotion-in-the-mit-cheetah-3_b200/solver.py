@@ -116,6 +116,8 @@ class BatchedMPC:
             if tuple(t.shape) != shp or t.dtype != dt or not t.is_contiguous() or not t.is_cuda:
                 raise ValueError(f"expected contiguous CUDA {dt} tensor of shape {shp}, got "
                                  f"{tuple(t.shape)} {t.dtype} cuda={t.is_cuda}")
+            if t.device.index != self.device:
+                raise ValueError(f"tensor on cuda:{t.device.index}, but this solver lives on cuda:{self.device}")
 
     def condense(self, x0, r, mask, x_des):
         """Dense condensed QP (H [B,12N,12N], g [B,12N]) as device tensors."""
@@ -149,6 +151,13 @@ class BatchedMPC:
         return U, X, SolveStats(iters, pri, dua, status)
 
     # -- warm-start state ---------------------------------------------------------------
+    def reset_warm_async(self, B=None, slot0=0, slot_mask=None, stream=None):
+        """Stream-ordered reset of slots [slot0, slot0+B); `slot_mask` = uint8 device tensor of B bytes."""
+        import torch
+        B = self.max_batch - slot0 if B is None else B
+        s = torch.cuda.current_stream(torch.device("cuda", self.device)).cuda_stream if stream is None else stream
+        _capi.check(_capi.lib().cmpc_reset_warm_async(self._h, B, slot0, _ptr(slot_mask), C.c_void_p(s)))
+
     def reset_warm(self, slot_mask=None):
         if slot_mask is None:
             _capi.check(_capi.lib().cmpc_reset_warm(self._h, None))

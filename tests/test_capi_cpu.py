@@ -46,12 +46,40 @@ def test_supported_horizons_and_version():
     assert _capi.lib().cmpc_version() == 1
 
 
+def test_any_horizon_maps_to_a_compiled_kernel():
+    """reference src/main.py:41 accepts any params['N']: horizons without their own kernel run
+    padded on the next compiled one."""
+    hs = _capi.supported_horizons()
+    assert _capi.lib().cmpc_max_horizon() == max(hs) == 60
+    for N in range(1, 61):
+        k = _capi.kernel_horizon(N)
+        assert k in hs and k >= N and not any(N <= h < k for h in hs)
+    with pytest.raises(pkg.CmpcError):
+        _capi.kernel_horizon(61)
+    assert _capi.has_variant(10, 0) and _capi.has_variant(30, 2) and not _capi.has_variant(10, 7)
+
+
+def test_alias_package_is_one_module():
+    """`mpc_b200.<sub>` must be the same module objects as the hyphen-named package's."""
+    import importlib
+    import mpc_b200.gait
+    import mpc_b200.solver
+    from mpc_b200.gait import GaitPlan
+    real = importlib.import_module("mpc-for-dynamic-locomotion-in-the-mit-cheetah-3_b200")
+    assert GaitPlan is pkg.GaitPlan is real.gait.GaitPlan
+    assert mpc_b200.solver.MPC is pkg.MPC and mpc_b200.solver is real.solver
+    assert pkg._capi is real._capi and pkg.CmpcError is real._capi.CmpcError
+
+
 def test_argument_validation_without_touching_the_gpu():
     L = _capi.lib()
     h = C.c_void_p()
-    cfg = _capi.default_config(7, 16)            # no kernel for N=7
+    cfg = _capi.default_config(61, 16)           # beyond the largest compiled kernel
     assert L.cmpc_create(C.byref(cfg), C.byref(h)) == -3
-    assert b"N=7" in L.cmpc_last_error()
+    assert b"N=61" in L.cmpc_last_error()
+    cfg = _capi.default_config(10, 16)
+    cfg.cache_factorization, cfg.check_every, cfg.refresh_every = 1, 5, 3
+    assert L.cmpc_create(C.byref(cfg), C.byref(h)) == -1
     cfg = _capi.default_config(10, 0)
     assert L.cmpc_create(C.byref(cfg), C.byref(h)) == -1
     cfg = _capi.default_config(10, 16)

@@ -19,6 +19,8 @@ from test_gpu_parity import gpu_solve, close, ATOL, RTOL, _FakeLite3, _Logger   
                                              (10, 3, GAIT_NAMES), (10, 4, GAIT_NAMES), (30, 0, ("trot",)),
                                              (30, 1, GAIT_NAMES), (30, 3, ("trot",)), (30, 4, GAIT_NAMES)])
 def test_cluster_kernel_iterate_parity(N, variant, gaits):
+    if not pkg._capi.has_variant(N, variant):
+        pytest.skip("layout variant needs a build with -DCMPC_EXTRA_LAYOUTS")
     B, K = 6, (50 if N < 60 else 120)
     pb = synthetic_batch(B, N=N, gaits=gaits, seed=3)
     out = gpu_solve(pb, max_iter=K, check_every=100000, eps_abs=0.0, eps_rel=0.0, warm_mode=0,

@@ -222,3 +222,49 @@ def test_closed_loop_with_factorisation_cache_tracks_like_without():
     assert abs(sb["rms_pos_err"] - sa["rms_pos_err"]) < 2e-4 and abs(sb["rms_ang_err"] - sa["rms_ang_err"]) < 5e-4
     xa, xb = a.x.cpu().numpy(), b.x.cpu().numpy()
     assert np.abs(xa[:, :12] - xb[:, :12]).max() < 2e-3
+
+
+# ------------------------------------------------------------------------------------------
+# SURVEY.md 8f.1 pinned on the reference: cmpc_assemble against fixtures recorded from the
+# reference's own planner / swing generator (tests/golden/gait_golden.npz)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["trot", "pseudo_gallop", "pseudo_gallop_ds4", "amble", "pronk",
+                                  "trot_turning", "trot_ss7", "stand"])
+def test_assemble_matches_reference_planner_fixtures(gait_gold, name):
+    """Contact masks bit-exact with reference get_phase_at_time (src/footstep_planner.py:226-246)
+    and look-ahead feet (src/mpc.py:306-318 + src/foot_trajectory_generator.py:27-96) to fp32
+    rounding, for every tick of the recorded schedule and past its end."""
+    g = lambda k: gait_gold[f"{name}/{k}"]
+    N = 10
+    pos, fid = g("pos"), g("feet_id")                    # the reference planner's own plan
+    S, T = pos.shape[0], g("mask").shape[0]
+    dev = torch.device("cuda", 0)
+    mpc = pkg.BatchedMPC(N=N, max_batch=1)
+    f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    plan_pos = f32(pos[None])
+    feet_id = torch.from_numpy(pkg.stance_bits(fid)[None].copy()).to(dev)
+    ss = torch.tensor([int(g("ss"))], dtype=torch.int32, device=dev)
+    ds = torch.tensor([int(g("ds"))], dtype=torch.int32, device=dev)
+    zero3, zero1, zero2 = f32(np.zeros((1, 3))), f32(np.zeros(1)), f32(np.zeros((1, 2)))
+    gt = _capi.GaitTables(plan_pos=plan_pos.data_ptr(), feet_id=feet_id.data_ptr(), ss=ss.data_ptr(),
+                          ds=ds.data_ptr(), v_ref=zero3.data_ptr(), omega_ref=zero1.data_ptr(),
+                          rp0=zero2.data_ptr(), S=S, total_steps=int(g("total_steps")), step_height=0.08,
+                          g=GRAVITY)
+    x = f32(np.zeros((1, 13)))                           # com at the origin: r = foot position
+    x_des = torch.empty((1, N + 1, 13), dtype=torch.float32, device=dev)
+    r = torch.empty((1, N, 4, 3), dtype=torch.float32, device=dev)
+    mask = torch.empty((1, N), dtype=torch.uint8, device=dev)
+    tick = torch.zeros(1, dtype=torch.int32, device=dev)
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    worst = 0.0
+    for t in range(0, T - N):
+        tick.fill_(t)
+        _capi.check(_capi.lib().cmpc_assemble(mpc._h, 1, C.byref(gt), _ptr(tick), _ptr(x), _ptr(zero1),
+                                              _ptr(zero3), _ptr(x_des), _ptr(r), _ptr(mask), s))
+        torch.cuda.synchronize()
+        assert np.array_equal(mask.cpu().numpy()[0], pkg.stance_bits(g("mask")[t:t + N])), t    # bit-exact
+        foot = g("foot")[t:t + N]
+        err = np.abs(r.cpu().numpy()[0].astype(np.float64) - foot)
+        worst = max(worst, err.max())
+        assert err.max() <= 2.5e-7, (t, err.max())        # ~1 ulp of fp32 at the feet's 0.5-2 m range
+    print(f"{name}: worst |foot_gpu - foot_reference| = {worst:.2e} m over {T - N} ticks")

@@ -1,0 +1,111 @@
+"""Tight parity of the CUDA path (through the C ABI) with the pinned oracle, on every BASELINE
+config, at the north-star tolerance (BASELINE.json): per-stage net wrench within
+1e-2 N (N m) absolute + 1e-3 relative of a tight-tolerance fp64 solve of the reference's QP
+(src/mpc.py:64-173), state trajectory and objective likewise.  With the reference's zero force
+weight (src/mpc.py:121) the split of a stage's wrench over the legs is not unique,
+the wrench [sum f ; sum r x f], X and J are - those are compared; the strictly convex variant
+(r_weight > 0) compares the full force vector.
+
+Oracle chain: oracle/tight_ipm.py (interior point, every sampled problem) == oracle/osqp_ref.c run to
+eps 1e-10 (the restatement pinned on the reference's logged run) - checked here again on the first
+problems of every sample, and in tests/test_oracle_tight.py.  EVERY sampled problem counts: there is
+no skip."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import mpc_b200 as pkg                                               # noqa: E402
+from mpc_b200.problems import synthetic_batch, DT, GAIT_NAMES, ProblemBatch   # noqa: E402
+from oracle import srbd_qp, tight_ipm as ipm                          # noqa: E402
+from test_oracle_tight import osqp_tight, assert_same_optimum         # noqa: E402
+
+ATOL, RTOL = 1e-2, 1e-3
+
+
+def f32_64(a):
+    """The kernel sees fp32 inputs: the oracle gets the same rounded values."""
+    return np.float32(a).astype(np.float64)
+
+
+def tight_gpu(pb, sel, K, **opts):
+    """The CUDA ADMM run for K iterations without early exit on the selected problems."""
+    dev = torch.device("cuda", 0)
+    args = [torch.from_numpy(np.ascontiguousarray(a[sel])).to(dev) for a in pb.f32()]
+    mpc = pkg.BatchedMPC(N=pb.N, max_batch=len(sel), max_iter=K, check_every=25, eps_abs=0.0, eps_rel=0.0,
+                         warm_mode=0, **opts)
+    U, X, st = mpc.solve(*args)
+    torch.cuda.synchronize()
+    assert np.all(st.status.cpu().numpy() == 0)          # ran the full budget, stayed finite
+    return U.cpu().numpy().astype(np.float64), X.cpu().numpy().astype(np.float64)
+
+
+def check_sample(pb, sel, K, n_osqp=2, x_atol=5e-5, j_rtol=1e-5, **opts):
+    U, X = tight_gpu(pb, sel, K, **opts)
+    worst = 0.0
+    for i, b in enumerate(sel):
+        x0, r, st, xd, mu = pb.problem(b)
+        x0, r, xd, mu = f32_64(x0), f32_64(r), f32_64(xd), float(np.float32(mu))
+        ref = ipm.solve_problem(x0, r, st, xd, mu, DT)
+        if i < n_osqp:                                    # the pinned oracle agrees on this very problem
+            assert_same_optimum(ref, *osqp_tight(x0, r, st, xd, mu)[:3])
+        W = srbd_qp.stage_wrench(U[i], r)
+        dW = np.abs(W - ref["wrench"])
+        worst = max(worst, float((dW / (ATOL + RTOL * np.abs(ref["wrench"]))).max()))
+        assert np.all(dW <= ATOL + RTOL * np.abs(ref["wrench"])), (b, dW.max())
+        assert np.all(np.abs(X[i].T - ref["X"]) <= x_atol + RTOL * np.abs(ref["X"])), (b, np.abs(X[i].T - ref["X"]).max())
+        J = srbd_qp.objective(X[i].T, xd)
+        assert abs(J / ref["J"] - 1.0) <= j_rtol, (b, J, ref["J"])
+        sw = np.repeat(st.reshape(-1) == 0, 3)            # swing legs exactly zero (src/mpc.py:138-144)
+        assert np.all(U[i].reshape(-1)[sw] == 0.0)
+    return worst
+
+
+def test_tight_parity_config2():
+    """config 2: 32 problems sampled from the 4096-problem trot batch of bench.py (seed 0)."""
+    pb = synthetic_batch(4096, N=10, seed=0)
+    sel = np.random.default_rng(2).choice(pb.B, 32, replace=False)
+    worst = check_sample(pb, sel, K=4000)
+    print(f"config 2: worst wrench error = {worst:.3f} of the north-star tolerance")
+
+
+def test_tight_parity_config3_mixed_gaits_mu_sweep():
+    """config 3: 4 gaits, mu in [0.3, 1], 40 problems incl. every pronk problem of the sample whose
+    horizon holds a flight stage (no stance leg)."""
+    pb = synthetic_batch(8192, N=10, gaits=GAIT_NAMES, seed=0, mu=(0.3, 1.0))
+    rng = np.random.default_rng(3)
+    sel = list(rng.choice(pb.B, 32, replace=False))
+    flight = np.where((pb.stance.sum(-1) == 0).any(1))[0]
+    assert len(flight) > 0
+    sel += list(flight[:8])
+    assert {int(g) for g in pb.gait_id[sel]} == {0, 1, 2, 3}
+    worst = check_sample(pb, np.array(sel), K=30000)
+    print(f"config 3: worst wrench error = {worst:.3f} of the north-star tolerance")
+
+
+def test_tight_parity_config4_long_horizon():
+    """config 4: N = 30 trot, 24 problems sampled from the 16384-problem batch."""
+    pb = synthetic_batch(16384, N=30, seed=0)
+    sel = np.random.default_rng(4).choice(pb.B, 24, replace=False)
+    worst = check_sample(pb, sel, K=60000, n_osqp=1)
+    print(f"config 4: worst wrench error = {worst:.3f} of the north-star tolerance")
+
+
+@pytest.mark.parametrize("N", [5, 20])
+def test_tight_parity_other_horizons(N):
+    pb = synthetic_batch(64, N=N, gaits=GAIT_NAMES, seed=6, mu=(0.3, 1.0))
+    check_sample(pb, np.arange(12), K=30000, n_osqp=1)
+
+
+def test_tight_parity_full_forces_with_force_weight():
+    """With a force weight the optimum is unique: the FULL force vector against the tight optimum at
+    |dU| <= 1e-2 N + 1e-3 |U| on every problem (no skip)."""
+    rw = 1e-2
+    pb = synthetic_batch(64, N=10, gaits=GAIT_NAMES, seed=35, mu=(0.3, 1.0))
+    sel = np.arange(24)
+    U, X = tight_gpu(pb, sel, 30000, r_weight=rw)
+    for i, b in enumerate(sel):
+        x0, r, st, xd, mu = pb.problem(b)
+        ref = ipm.solve_problem(f32_64(x0), f32_64(r), st, f32_64(xd), float(np.float32(mu)), DT, r_weight=rw)
+        assert np.all(np.abs(U[i] - ref["U"]) <= ATOL + RTOL * np.abs(ref["U"])), (b, np.abs(U[i] - ref["U"]).max())

@@ -7,10 +7,14 @@ A "step" is one pass of the hot path (condense + factor + ADMM, cold start) over
 of 4096 synthetic problems per GPU.  One process per GPU
 (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); problems shard by batch index with no
 collective on the solve path ("weak" scaling: 4096 problems per GPU).  Rank 0 prints one
-JSON line.  `--impl reference` times the reference's CPU algorithm (OSQP restatement in C,
-oracle/) on the host cores on a bounded sample of the same workload.
+JSON line; its `configs` block carries the other BASELINE configs (3: 65536 mixed-gait problems
+sharded over the ranks, 4: N=30 x 16384 per GPU, 5: closed-loop rollouts) and `sharding_check`
+the bit-identity of a batch solved sharded over the ranks (NCCL gather) against one GPU.
+`--impl reference` times the reference's CPU algorithm (OSQP restatement in C, oracle/) on the
+host cores on the FULL 4096-problem batch of the same workload.
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -26,10 +30,8 @@ import numpy as np  # noqa: E402
 
 BATCH = 4096
 HORIZON = 10
-KERNEL_NAMES = {10: "cmpc::solve_kernel<10,1,8,1,false>", 20: "cmpc::solve_kernel<20,2,2,1,false>",
-                30: "cmpc::solve_kernel<30,6,1,3,false>", 40: "cmpc::solve_cluster_kernel<10,4,4,1>",
-                60: "cmpc::solve_cluster_kernel<10,6,6,1>"}
 WORKLOAD = "config2: batch 4096 Lite3 trot MPC QPs per GPU, N=10, randomized CoM states/velocity refs, cold start"
+KERNEL_SRC = os.path.join(ROOT, "mpc-for-dynamic-locomotion-in-the-mit-cheetah-3_b200", "csrc", "cmpc_kernels.cuh")
 
 
 def parse():
@@ -41,8 +43,10 @@ def parse():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--horizon", type=int, default=HORIZON)
     ap.add_argument("--gaits", default="trot")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="problems per CPU step (0 = the full batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs 3/4/5 block")
+    ap.add_argument("--rollout-ticks", type=int, default=1000)
     return ap.parse_args()
 
 
@@ -52,6 +56,13 @@ def measured_peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def kernel_source_sha():
+    try:
+        return hashlib.sha256(open(KERNEL_SRC, "rb").read()).hexdigest()[:16]
+    except OSError:
+        return None
 
 
 class ClockSampler:
@@ -115,17 +126,18 @@ def algorithmic_work(N, stance_counts, iters):
 
 # ------------------------------------------------------------------------------------------
 def run_reference(args):
-    """Reference arm: the reference's CPU algorithm (fp64 OSQP restatement, oracle/) on the
-    host cores, bounded sample of the same workload."""
+    """Reference arm: the reference's CPU algorithm (fp64 OSQP restatement, oracle/) on all host
+    threads; each step solves the FULL batch of the workload (same config as our arm)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import cpu_baseline
     import mpc_b200 as pkg
-    sample = args.cpu_sample or 256
-    pb = pkg.problems.synthetic_batch(sample, N=args.horizon, gaits=tuple(args.gaits.split(",")), seed=0)
-    for _ in range(max(args.warmup, 1)):
-        cpu_baseline.solve_batch(pb.slice(0, min(32, sample)))
+    sample = args.cpu_sample or args.batch
+    pb = pkg.problems.synthetic_batch(args.batch, N=args.horizon, gaits=tuple(args.gaits.split(",")), seed=0)
+    pb = pb.slice(0, sample)
+    for _ in range(max(min(args.warmup, 2), 1)):
+        cpu_baseline.solve_batch(pb.slice(0, min(256, sample)))
     times = []
     for _ in range(args.steps):
         t0 = time.perf_counter()
@@ -133,18 +145,175 @@ def run_reference(args):
         times.append(time.perf_counter() - t0)
     tot = sum(times)
     val = sample * args.steps / tot
+    what = "the full batch" if sample == args.batch else f"{sample} of the {args.batch} problems"
     line = {
         "impl": "reference", "metric": "QP solves/sec", "value": val, "unit": "solves/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{sample} problems per step"},
+        "config": {"workload": WORKLOAD, "batch_per_step": sample, "horizon": args.horizon,
+                   "solved_frac": float((info["status"] == 1).mean())},
         "cpu_baseline": {"value": val, "unit": "solves/s", "cores": info["threads"],
-                         "kind": info["kind"], "sample": f"{sample} of the {args.batch} problems, "
-                         f"all {info['threads']} host threads, mean {info['mean_iters']:.1f} OSQP iterations"},
+                         "kind": info["kind"], "sample": f"{what} per step, all {info['threads']} host threads, "
+                         f"mean {info['mean_iters']:.1f} OSQP iterations"},
         "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+class Bench:
+    """Timing helpers of one rank."""
+
+    def __init__(self, torch, dist, dev, world):
+        self.torch, self.dist, self.dev, self.world = torch, dist, dev, world
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        self.stream = torch.cuda.current_stream(dev)
+
+    def barrier(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def timed_steps(self, fn, steps, warmup=3, pre=None):
+        """Per-step CUDA-event times (ms) of fn(); L2 flushed (256 MiB fill) before every step."""
+        torch = self.torch
+        for _ in range(warmup):
+            if pre:
+                pre()
+            fn()
+        self.barrier()
+        evs = []
+        for _ in range(steps):
+            if pre:
+                pre()
+            self.flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            fn()
+            e1.record(self.stream)
+            evs.append((e0, e1))
+        self.barrier()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    def max_over_ranks(self, vals):
+        t = self.torch.tensor(vals, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def gather(self, vals):
+        """[world][len(vals)] on every rank."""
+        t = self.torch.tensor(vals, dtype=self.torch.float64, device=self.dev)
+        if self.world == 1:
+            return [[float(v) for v in t]]
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [[float(v) for v in o] for o in out]
+
+
+def kernel_times(pkg, bench, N, B, local, dargs, out, steps, **opts):
+    """Duration of the solve kernel alone: CUDA events recorded by the library on the launching
+    stream immediately around that one kernel (cfg.time_kernel), L2 flushed between steps."""
+    mpc_t = pkg.BatchedMPC(N=N, max_batch=B, device=local, warm_mode=0, time_kernel=1, **opts)
+    ms = []
+    for i in range(steps + 3):
+        bench.flush.fill_(1)
+        mpc_t.solve(*dargs, out=out)
+        if i >= 3:
+            ms.append(mpc_t.last_kernel_ms)
+    bench.barrier()
+    mpc_t.close()
+    return ms
+
+
+def per_rank_block(bench, kern_ms, step_ms, iters):
+    rows = bench.gather([statistics.mean(kern_ms), statistics.mean(step_ms), float(iters.max()), float(iters.mean())])
+    k = [r[0] for r in rows]
+    return {"kernel_ms": {"min": min(k), "median": statistics.median(k), "max": max(k), "per_rank": k},
+            "step_ms_per_rank": [r[1] for r in rows], "max_iters_per_rank": [int(r[2]) for r in rows],
+            "mean_iters_per_rank": [r[3] for r in rows]}
+
+
+def fp32_frac(flops, B, kern_s, fp32_peak):
+    return flops * B / kern_s / fp32_peak
+
+
+def run_config(pkg, bench, torch, local, rank, world, name, pb, steps, fp32_peak, scaling, global_batch=None):
+    """Cold-start solves/s of one more BASELINE config on this rank's problems `pb`."""
+    dev = bench.dev
+    B, N = pb.B, pb.N
+    dargs = [torch.from_numpy(a).to(dev) for a in pb.f32()]
+    mpc = pkg.BatchedMPC(N=N, max_batch=B, device=local, warm_mode=0)
+    out = mpc.alloc_outputs(B, want_X=True, device=dev)
+    step_ms = bench.timed_steps(lambda: mpc.solve(*dargs, out=out), steps)
+    iters = out[2].cpu().numpy()
+    status = out[5].cpu().numpy()
+    mpc.close()
+    kern_ms = kernel_times(pkg, bench, N, B, local, dargs, out, steps)
+    tmax, = bench.max_over_ranks([sum(step_ms)])
+    ranks = per_rank_block(bench, kern_ms, step_ms, iters)
+    flops, smem_b, hbm_b = algorithmic_work(N, pb.stance.sum((1, 2)), iters)
+    total = (global_batch if global_batch is not None else B * world) * steps
+    return {"workload": name, "value": total / (tmax * 1e-3), "unit": "solves/s", "scaling": scaling,
+            "batch_this_rank": B, "horizon": N, "ms_per_step": tmax / steps,
+            "kernel_ms": statistics.mean(kern_ms),
+            "fp32_frac": fp32_frac(flops, B, statistics.mean(kern_ms) * 1e-3, fp32_peak),
+            "algorithmic_flop_per_solve": flops, "mean_iters": float(iters.mean()), "max_iters": int(iters.max()),
+            "solved_frac": float((status == 1).mean()), "per_rank": ranks}
+
+
+def sharding_check(pkg, bench, torch, dist, local, rank, world):
+    """ONE global batch solved as `world` contiguous shards (one per GPU), the
+    results gathered over NCCL with sharding.gather_results, must equal bit for bit what one GPU
+    returns for the whole batch (rank 0 solves it alone as the comparison)."""
+    Bg, N = 8192, 10
+    pb = pkg.problems.synthetic_batch(Bg, N=N, gaits=pkg.problems.GAIT_NAMES, seed=123, mu=(0.3, 1.0))
+    mpc = pkg.BatchedMPC(N=N, max_batch=Bg, device=local, warm_mode=0)
+    lo, hi, U, X, st = pkg.sharding.solve_sharded(mpc, pb, rank, world, device=bench.dev)
+    u0 = U[:, 0, :].contiguous()
+    if world > 1:
+        g_u0, g_it, g_st = pkg.sharding.gather_results(u0, st.iters, st.status, Bg)
+    else:
+        g_u0, g_it, g_st = u0, st.iters, st.status
+    res = None
+    if rank == 0:
+        full = [torch.from_numpy(a).to(bench.dev) for a in pb.f32()]
+        Uf, _, sf = mpc.solve(*full)
+        torch.cuda.synchronize(bench.dev)
+        res = {"global_batch": Bg, "shards": world,
+               "gather": "sharding.gather_results over NCCL all_gather" if world > 1 else "single rank (no gather)",
+               "bit_identical_u0": bool(torch.equal(g_u0, Uf[:, 0, :])),
+               "identical_iters": bool(torch.equal(g_it, sf.iters)),
+               "identical_status": bool(torch.equal(g_st, sf.status))}
+    bench.barrier()
+    mpc.close()
+    return res
+
+
+def run_rollout(pkg, bench, torch, local, world, ticks):
+    """config 5: closed-loop warm-started rollouts, 8192 robots per GPU, friction sweep 0.3-1.0."""
+    B = 8192
+    ro = pkg.ClosedLoopRollout(B, N=10, gaits=("trot",), mu=(0.3, 1.0), seed=0, device=local)
+    ro.capture(10)
+    bench.barrier()
+    l0 = ro.mpc.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    done0 = int(ro.tick.item())
+    e0.record(bench.stream)
+    ro.run(ticks)
+    e1.record(bench.stream)
+    bench.barrier()
+    ms = e0.elapsed_time(e1)
+    n = int(ro.tick.item()) - done0
+    s = ro.summary()
+    tmax, = bench.max_over_ranks([ms])
+    return {"workload": f"config5: closed-loop warm-started rollouts, {B} robots per GPU x {n} ticks, mu sweep 0.3-1.0, "
+                        "SRBD plant (DART unavailable), CUDA graph of 10 ticks",
+            "value": B * world * n / (tmax * 1e-3), "unit": "robot-ticks/s", "scaling": "weak",
+            "ms_per_tick": tmax / max(n, 1), "ticks": n, "mean_iters": s["mean_iters"], "unsolved": s["unsolved"],
+            "cache_hit_frac": s["cache_hit_frac"], "rms_pos_err_m": s["rms_pos_err"], "finite": s["finite"],
+            "graph_replays_count_as_launches": int(ro.mpc.launch_count - l0)}
 
 
 def run_ours(args):
@@ -161,6 +330,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    bench = Bench(torch, dist, dev, world)
     B, N = args.batch, args.horizon
     gaits = tuple(args.gaits.split(","))
     # every rank draws its own shard of the global batch (batch-index sharding, no exchange)
@@ -170,52 +340,24 @@ def run_ours(args):
     dargs = [t.to(dev) for t in pinned]
     mpc = pkg.BatchedMPC(N=N, max_batch=B, device=local, warm_mode=0)
     out = mpc.alloc_outputs(B, want_X=True, device=dev)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    stream = torch.cuda.current_stream(dev)
+    stream = bench.stream
     for _ in range(max(args.warmup, 3)):
         mpc.solve(*dargs, out=out)
-    barrier()
+    bench.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = mpc.launch_count
     # --- kernel-resident timing: inputs already in HBM, per-step CUDA events, L2 flushed ----
-    evs = []
-    barrier()
     t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.fill_(1)                      # evict inputs / warm state from the 126 MB L2
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        mpc.solve(*dargs, out=out)
-        e1.record(stream)
-        evs.append((e0, e1))
-    barrier()
+    step_ms = bench.timed_steps(lambda: mpc.solve(*dargs, out=out), args.steps, warmup=0)
     t_wall = time.perf_counter() - t_wall0
-    step_ms = [a.elapsed_time(b) for a, b in evs]
     launches = mpc.launch_count - l0
     dev_ms = sum(step_ms)
     iters = out[2].cpu().numpy()
     status = out[5].cpu().numpy()
 
-    # --- the solve kernel alone (roofline denominator): CUDA events recorded by the library on the
-    # launching stream immediately around that one kernel, same inputs, L2 flushed between steps
-    mpc_t = pkg.BatchedMPC(N=N, max_batch=B, device=local, warm_mode=0, time_kernel=1)
-    kern_ms = []
-    for i in range(args.steps + 3):
-        flush.fill_(1)
-        mpc_t.solve(*dargs, out=out)
-        if i >= 3:
-            kern_ms.append(mpc_t.last_kernel_ms)
-    barrier()
-    mpc_t.close()
+    kern_ms = kernel_times(pkg, bench, N, B, local, dargs, out, args.steps)
 
     # --- warm start: x of the same problems one tick earlier, y = 0 (the
     # reference's semantics, src/mpc.py:270-271).  The previous-tick solve and the restore of the
@@ -230,7 +372,7 @@ def run_ours(args):
     warm_ms = []
     for i in range(args.steps + 3):
         mpc_w.set_warm(x_prev)
-        flush.fill_(1)
+        bench.flush.fill_(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         mpc_w.solve(*dargs, out=out_w)
@@ -240,7 +382,7 @@ def run_ours(args):
             warm_ms.append(e0.elapsed_time(e1))
     warm_iters = out_w[2].cpu().numpy()
     warm_status = out_w[5].cpu().numpy()
-    barrier()
+    bench.barrier()
     mpc_w.close()
 
     # --- end to end: host (pinned) buffers through cmpc_solve_host, copies inside the timing ----
@@ -250,13 +392,13 @@ def run_ours(args):
             pin((B,), torch.float32), pin((B,), torch.float32), pin((B,), torch.int32))
     for _ in range(3):
         mpc.solve_host(*hin, want_X=False, out=hout)
-    barrier()
+    bench.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         mpc.solve_host(*hin, want_X=False, out=hout)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
-    barrier()
+    bench.barrier()
     clocks = sampler.stop() if rank == 0 else None
 
     # --- latency: B=1 end-to-end p50, batch wall p50 ----------------------------------------
@@ -278,10 +420,38 @@ def run_ours(args):
                "batch_amortised_p50_us_per_solve": 1e3 * statistics.median(step_ms) / B}
 
     # --- reduce over ranks: max time ------------------------------------------------------------
-    tt = torch.tensor([dev_ms, e2e_s, sum(warm_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_s_max, warm_ms_max = float(tt[0]), float(tt[1]), float(tt[2])
+    dev_ms_max, e2e_s_max, warm_ms_max = bench.max_over_ranks([dev_ms, e2e_s, sum(warm_ms)])
+    ranks = per_rank_block(bench, kern_ms, step_ms, iters)
+
+    try:
+        fp32_peak = pkg._capi.fp32_peak(local) * 1e12
+        fp32_src = "measured in this run (cmpc_fp32_peak: 8-chain FMA kernel, best of 4)"
+    except Exception:
+        fp32_peak = 148 * 128 * 2 * 1.965e9
+        fp32_src = "148 SM x 128 lanes x 2 x 1.965 GHz (nominal)"
+
+    # --- the other BASELINE configs and the sharded-identity check (all ranks take part) ----------
+    configs = {}
+    shard = None
+    if not args.no_configs:
+        P = pkg.problems
+        lo, hi = pkg.sharding.shard_range(65536, rank, world)
+        pb3 = P.synthetic_batch(65536, N=10, gaits=P.GAIT_NAMES, seed=0, mu=(0.3, 1.0)).slice(lo, hi)
+        configs["config3"] = run_config(
+            pkg, bench, torch, local, rank, world,
+            f"config3: ONE global batch of 65536 mixed-gait problems (trot/pronk/amble/pseudo-gallop, mu 0.3-1.0), "
+            f"N=10, contiguous batch-index shards over {world} GPU(s), cold start",
+            pb3, max(args.steps // 3, 5), fp32_peak, "strong", global_batch=65536)
+        del pb3
+        pb4 = P.synthetic_batch(16384, N=30, gaits=("trot",), seed=rank)
+        configs["config4"] = run_config(
+            pkg, bench, torch, local, rank, world,
+            "config4: long horizon N=30 trot, 16384 problems per GPU, cold start",
+            pb4, max(args.steps // 6, 3), fp32_peak, "weak")
+        pb4_cpu = pb4.slice(0, 256)
+        del pb4
+        configs["config5"] = run_rollout(pkg, bench, torch, local, world, args.rollout_ticks)
+        shard = sharding_check(pkg, bench, torch, dist, local, rank, world)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -294,29 +464,45 @@ def run_ours(args):
     flops, smem_b, hbm_b = algorithmic_work(N, pb.stance.sum((1, 2)), iters)
     kern_s = statistics.mean(kern_ms) * 1e-3         # this rank's mean solve-kernel launch duration
     ach_gbs = hbm_b * B / kern_s / 1e9
-    traffic = None
+    # DRAM traffic and the shared-memory pipe share come from the committed ncu capture; they are
+    # quoted only while the kernel source is the one that was profiled
+    traffic, ncu_note, smem_pipe_pct = None, "no ncu capture on record", None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp) and (B, N, gaits) == (BATCH, HORIZON, ("trot",)):   # captured on this workload only
-        traffic = json.load(open(tp)).get("solve_kernel_dram_bytes_per_launch")
-    try:
-        fp32_peak = pkg._capi.fp32_peak(local) * 1e12
-        fp32_src = "measured in this run (cmpc_fp32_peak: 8-chain FMA kernel, best of 4)"
-    except Exception:
-        fp32_peak = 148 * 128 * 2 * 1.965e9
-        fp32_src = "148 SM x 128 lanes x 2 x 1.965 GHz (nominal)"
+    if os.path.exists(tp) and (B, N, gaits) == (BATCH, HORIZON, ("trot",)):
+        tj = json.load(open(tp))
+        if tj.get("kernel_source_sha") in (None, kernel_source_sha()):
+            traffic = tj.get("solve_kernel_dram_bytes_per_launch")
+            smem_pipe_pct = tj.get("smem_pipe_pct_of_peak")
+            ncu_note = tj.get("source", "profiles/traffic.json")
+        else:
+            ncu_note = "profiles/traffic.json was captured on an older kernel source: not quoted"
     smem_peak = 148 * 128 * 1.965e9
-    roof = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-            "frac": ach_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-            "kernel": KERNEL_NAMES.get(N, f"cmpc::solve_kernel<{N},...>"), "algorithmic_bytes_per_solve": hbm_b,
-            "kernel_ms": statistics.mean(kern_ms), "kernel_share_of_step": statistics.mean(kern_ms) / (dev_ms / args.steps),
+    fr_fp32 = flops * B / kern_s / fp32_peak
+    fr_smem = smem_b * B / kern_s / smem_peak
+    fr_hbm = ach_gbs / hbm_peak
+    kname = f"cmpc::solve_kernel (N={N})" if N <= 30 else f"cmpc::solve_cluster_kernel (N={N})"
+    # the roofline fraction is the LARGEST of the three (FP32 pipe, shared memory, HBM)
+    binding = max((fr_fp32, "fp32"), (fr_hbm, "hbm"))
+    roof = {"bound": binding[1],
+            "achieved": flops * B / kern_s / 1e12 if binding[1] == "fp32" else ach_gbs,
+            "peak": fp32_peak / 1e12 if binding[1] == "fp32" else hbm_peak,
+            "unit": "TFLOP/s" if binding[1] == "fp32" else "GB/s",
+            "frac": binding[0], "traffic": traffic, "traffic_source": ncu_note,
+            "peak_source": fp32_src if binding[1] == "fp32" else peak_src,
+            "kernel": kname, "kernel_ms": statistics.mean(kern_ms),
+            "kernel_share_of_step": statistics.mean(kern_ms) / (dev_ms / args.steps),
             "timing": "cudaEvent pair recorded by libcmpc on the launching stream around the solve kernel only "
                       "(cfg.time_kernel), mean over the timed steps of a second pass with the same inputs",
-            "note": "HBM is NOT the binding roof of this kernel (SURVEY.md 8d): on-chip fractions follow",
+            "note": "on-chip bound path (SURVEY.md 8d): the binding roof is the FP32 FMA pipe with the survey's "
+                    "algorithmic FLOP model; the HBM and shared-memory fractions are listed beside it",
             "fp32": {"algorithmic_flop_per_solve": flops, "achieved_tflops": flops * B / kern_s / 1e12,
-                     "peak_tflops": fp32_peak / 1e12, "frac": flops * B / kern_s / fp32_peak,
-                     "peak_source": fp32_src},
-            "smem": {"algorithmic_bytes_per_solve": smem_b, "achieved_tbs": smem_b * B / kern_s / 1e12,
-                     "peak_tbs": smem_peak / 1e12, "frac": smem_b * B / kern_s / smem_peak}}
+                     "peak_tflops": fp32_peak / 1e12, "frac": fr_fp32, "peak_source": fp32_src},
+            "hbm": {"algorithmic_bytes_per_solve": hbm_b, "achieved_gbs": ach_gbs, "peak_gbs": hbm_peak,
+                    "frac": fr_hbm, "peak_source": peak_src},
+            "smem": {"model_bytes_per_solve": smem_b, "model_frac_of_nominal_37TBs": fr_smem,
+                     "ncu_smem_pipe_pct_of_peak": smem_pipe_pct,
+                     "note": "the survey's 4Kn^2-byte model is of a triangular-solve algorithm this kernel does "
+                             "not run; the ncu figure is the measured shared-memory pipe utilisation"}}
     in_bytes = sum(a.nbytes for a in host)
     out_bytes = sum(a.nbytes for a in hout if a is not None)
     line = {
@@ -344,6 +530,9 @@ def run_ours(args):
                        "max_iters": int(warm_iters.max()), "solved_frac": float((warm_status == 1).mean()),
                        "what": "same batch warm-started with the forces of the same problems one tick earlier "
                                "(x unshifted, y = 0: the reference's set_initial semantics), L2 flushed, CUDA events"},
+        "per_rank": ranks,
+        "configs": configs,
+        "sharding_check": shard,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "latency": lat,
@@ -352,13 +541,18 @@ def run_ours(args):
     if not args.no_cpu_baseline and world == 1:
         try:
             from oracle import cpu_baseline
-            sample = args.cpu_sample or 192
+            sample = args.cpu_sample or B
             info = cpu_baseline.solve_batch(pb.slice(0, sample))
             line["cpu_baseline"] = {
                 "value": sample / info["seconds"], "unit": "solves/s", "cores": info["threads"],
                 "kind": info["kind"],
-                "sample": f"first {sample} of the {B} problems, {info['threads']} host threads, "
-                          f"mean {info['mean_iters']:.1f} OSQP iterations"}
+                "sample": (f"the full batch of {B} problems" if sample == B else f"first {sample} of the {B} problems")
+                          + f", {info['threads']} host threads, mean {info['mean_iters']:.1f} OSQP iterations"}
+            if not args.no_configs:
+                i4 = cpu_baseline.solve_batch(pb4_cpu)
+                line["cpu_baseline"]["config4_n30"] = {
+                    "value": pb4_cpu.B / i4["seconds"], "unit": "solves/s", "cores": i4["threads"],
+                    "sample": f"first {pb4_cpu.B} of the 16384 N=30 problems, mean {i4['mean_iters']:.1f} OSQP iterations"}
         except Exception as exc:      # the oracle is a checker; a missing build must not kill the bench
             line["cpu_baseline"] = {"value": None, "unit": "solves/s", "cores": 0, "kind": "port",
                                     "sample": f"unavailable: {exc}"}

@@ -207,6 +207,22 @@ int cmpc_leg_torques(cmpc_handle* h, int32_t B, const cmpc_gait_tables* gt, cons
                      const float* kp, const float* kd, float* tau, float* p_des, uint8_t* stance,
                      void* stream);
 
+/* Lite3 leg kinematics for B robots: everything cmpc_leg_torques needs that
+ * the reference reads from DART (src/main.py:203-214, 236-262, 286-350), in closed form from the
+ * joint tree of lite3_urdf/urdf/Lite3.urdf (hip offsets :45, thigh offset :73, link lengths :100,
+ * :122, axes :48, :76, :103, link masses / centres of mass).  DEVICE pointers: base_pos, theta
+ * (torso rotation vector = retrieve_state()['TORSO']['pos']), v_base, w_base [B,3] (world frame);
+ * q, dq [B,4,3] (HipX, HipY, Knee of FL, FR, HL, HR).  Outputs: foot_pos, foot_vel [B,4,3]; J, Jdot
+ * [B,4,3,3] world-frame linear Jacobian of the foot w.r.t. the leg's joints and its time derivative
+ * (getLinearJacobian / getJacobianClassicDeriv[3:] at the leg's columns); Mleg [B,4,3,3] =
+ * sum_i m_i J_com_i, the base-translation rows of the joint-space inertia matrix at the leg's
+ * columns (getMassMatrix()[3:6]); cg [B,4,3] gravity torques of the leg's joints (the velocity-product
+ * part of getCoriolisAndGravityForces is not modelled).  Mleg, cg may be NULL. */
+int cmpc_leg_kinematics(cmpc_handle* h, int32_t B, const float* base_pos, const float* theta,
+                        const float* v_base, const float* w_base, const float* q, const float* dq,
+                        float* foot_pos, float* foot_vel, float* J, float* Jdot, float* Mleg, float* cg,
+                        float gravity, void* stream);
+
 /* Measures the FP32 FMA throughput of `device` (TFLOP/s, best of 4 timed launches of an 8-chain
  * FMA kernel): the denominator of the on-chip roofline of the solve kernel. */
 int cmpc_fp32_peak(int32_t device, float* tflops);

@@ -26,7 +26,8 @@ SYMBOLS = ("cmpc_default_config", "cmpc_create", "cmpc_destroy", "cmpc_solve", "
            "cmpc_condense", "cmpc_reset_warm", "cmpc_get_warm", "cmpc_set_warm",
            "cmpc_launch_count", "cmpc_supported_horizons", "cmpc_version", "cmpc_last_error",
            "cmpc_assemble", "cmpc_plant_step", "cmpc_fp32_peak", "cmpc_leg_torques", "cmpc_last_kernel_ms", "cmpc_get_cache_meta", "cmpc_accumulate_stats",
-           "cmpc_reset_warm_async", "cmpc_max_horizon", "cmpc_kernel_horizon", "cmpc_has_variant")
+           "cmpc_reset_warm_async", "cmpc_max_horizon", "cmpc_kernel_horizon", "cmpc_has_variant",
+           "cmpc_leg_kinematics")
 
 
 class CmpcError(RuntimeError):
@@ -112,6 +113,7 @@ def lib() -> C.CDLL:
     L.cmpc_assemble.argtypes = [vp, i32, gtp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.cmpc_plant_step.argtypes = [vp, i32, gtp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.cmpc_leg_torques.argtypes = [vp, i32, gtp] + [vp] * 9 + [C.POINTER(C.c_float)] * 2 + [vp] * 4
+    L.cmpc_leg_kinematics.argtypes = [vp, i32] + [vp] * 12 + [C.c_float, vp]
     L.cmpc_fp32_peak.argtypes = [i32, C.POINTER(C.c_float)]
     L.cmpc_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.cmpc_get_cache_meta.argtypes = [vp, i32, i32, vp, vp]

@@ -51,3 +51,24 @@ class BatchedLegController:
             _ptr(cg), _ptr(dq), _ptr(foot_pos), _ptr(foot_vel), self.kp, self.kd, _ptr(tau),
             _ptr(p_des), _ptr(stance), C.c_void_p(s)))
         return tau, p_des, stance
+
+    def kinematics(self, base_pos, theta, v_base, w_base, q, dq, gravity=-9.81, with_dynamics=True, stream=None):
+        """Lite3 leg kinematics on the device (``cmpc_leg_kinematics``): base_pos, theta (torso rotation
+        vector), v_base, w_base [B,3]; q, dq [B,4,3] fp32 CUDA tensors.  Returns a dict of device
+        tensors foot_pos, foot_vel [B,4,3], J, Jdot [B,4,3,3] and, with ``with_dynamics``, Mleg [B,4,3,3]
+        and cg [B,4,3] - exactly the inputs :meth:`torques` takes."""
+        import torch
+        B = q.shape[0]
+        for name, t_, shape in (("base_pos", base_pos, (B, 3)), ("theta", theta, (B, 3)), ("v_base", v_base, (B, 3)),
+                                ("w_base", w_base, (B, 3)), ("q", q, (B, 4, 3)), ("dq", dq, (B, 4, 3))):
+            if tuple(t_.shape) != shape or t_.dtype != torch.float32 or not t_.is_contiguous() or not t_.is_cuda:
+                raise ValueError(f"{name}: expected a contiguous fp32 CUDA tensor of shape {shape}")
+        new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=q.device)
+        out = dict(foot_pos=new(B, 4, 3), foot_vel=new(B, 4, 3), J=new(B, 4, 3, 3), Jdot=new(B, 4, 3, 3),
+                   Mleg=new(B, 4, 3, 3) if with_dynamics else None, cg=new(B, 4, 3) if with_dynamics else None)
+        s = torch.cuda.current_stream(q.device).cuda_stream if stream is None else stream
+        _capi.check(_capi.lib().cmpc_leg_kinematics(
+            self.mpc._h, B, _ptr(base_pos), _ptr(theta), _ptr(v_base), _ptr(w_base), _ptr(q), _ptr(dq),
+            _ptr(out["foot_pos"]), _ptr(out["foot_vel"]), _ptr(out["J"]), _ptr(out["Jdot"]), _ptr(out["Mleg"]),
+            _ptr(out["cg"]), C.c_float(gravity), C.c_void_p(s)))
+        return out

@@ -753,6 +753,26 @@ int cmpc_leg_torques(cmpc_handle* h, int32_t B, const cmpc_gait_tables* gt, cons
   return CMPC_OK;
 }
 
+int cmpc_leg_kinematics(cmpc_handle* h, int32_t B, const float* base_pos, const float* theta,
+                        const float* v_base, const float* w_base, const float* q, const float* dq,
+                        float* foot_pos, float* foot_vel, float* J, float* Jdot, float* Mleg, float* cg,
+                        float gravity, void* stream) {
+  if (!h) return fail(CMPC_ERR_INVALID, "null handle");
+  if (B < 0) return fail(CMPC_ERR_INVALID, "negative batch");
+  if (B == 0) return CMPC_OK;
+  if (!base_pos || !theta || !v_base || !w_base || !q || !dq || !foot_pos || !foot_vel || !J || !Jdot)
+    return fail(CMPC_ERR_INVALID, "null pointer");
+  DEVICE_GUARD(h);
+  cmpc::KinParams p{};
+  p.base_pos = base_pos; p.theta = theta; p.v_base = v_base; p.w_base = w_base; p.q = q; p.dq = dq;
+  p.foot_pos = foot_pos; p.foot_vel = foot_vel; p.J = J; p.Jdot = Jdot; p.Mleg = Mleg; p.cg = cg;
+  p.B = B; p.g = gravity;
+  cmpc::leg_kinematics_kernel<<<(4 * B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  h->launches.fetch_add(1);
+  return CMPC_OK;
+}
+
 int cmpc_fp32_peak(int32_t device, float* tflops) {
   if (!tflops) return fail(CMPC_ERR_INVALID, "null pointer");
   int ndev = 0;

@@ -1400,6 +1400,145 @@ __global__ void __launch_bounds__(128) leg_torque_kernel(const LegParams p) {
   if (p.stance && l == 0) p.stance[b] = (uint8_t)bits;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Lite3 leg kinematics: what the reference reads from DART every tick
+// (src/main.py:203-214, 236-262, 286-350) in closed form from the joint tree of
+// lite3_urdf/urdf/Lite3.urdf (hip offsets :45/:143/:240/:337, roll axis -x :48, thigh offset :73,
+// pitch / knee axis -y :76/:103, thigh 0.20 :100, shank 0.21 :122; link masses / centres of mass
+// :32-33, :54-55, :82-83, :109).  One thread per (robot, leg): foot position / velocity, the
+// world-frame linear Jacobian of the foot w.r.t. the leg's 3 joints and its time derivative, the
+// base-translation rows of the joint-space inertia matrix at the leg's columns
+// (sum_i m_i J_com_i) and the gravity torques of the leg's joints.  Host mirror: kinematics.py.
+// Streaming: 21 floats in, 45 floats out per leg.
+// ---------------------------------------------------------------------------------------
+struct KinParams {
+  const float* __restrict__ base_pos;   // [B,3]
+  const float* __restrict__ theta;      // [B,3] torso rotation vector
+  const float* __restrict__ v_base;     // [B,3]
+  const float* __restrict__ w_base;     // [B,3] world-frame angular velocity
+  const float* __restrict__ q;          // [B,4,3] HipX, HipY, Knee
+  const float* __restrict__ dq;         // [B,4,3]
+  float* __restrict__ foot_pos;         // [B,4,3]
+  float* __restrict__ foot_vel;         // [B,4,3]
+  float* __restrict__ J;                // [B,4,3,3]
+  float* __restrict__ Jdot;             // [B,4,3,3]
+  float* __restrict__ Mleg;             // [B,4,3,3] nullable
+  float* __restrict__ cg;               // [B,4,3]   nullable
+  int32_t B;
+  float g;                              // gravity (negative, along z)
+};
+
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+struct M3 { float m[3][3]; };
+__device__ __forceinline__ V3 mul(const M3& R, V3 v) {
+  return {R.m[0][0] * v.x + R.m[0][1] * v.y + R.m[0][2] * v.z, R.m[1][0] * v.x + R.m[1][1] * v.y + R.m[1][2] * v.z,
+          R.m[2][0] * v.x + R.m[2][1] * v.y + R.m[2][2] * v.z};
+}
+
+__global__ void __launch_bounds__(128) leg_kinematics_kernel(const KinParams p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.B * 4) return;
+  const int b = idx >> 2, l = idx & 3;
+  const float sx = l < 2 ? 1.f : -1.f, sy = (l & 1) ? -1.f : 1.f;
+  // torso rotation exp([theta]x)
+  const float tx = p.theta[3 * b], ty = p.theta[3 * b + 1], tz = p.theta[3 * b + 2];
+  const float ang2 = tx * tx + ty * ty + tz * tz, ang = sqrtf(ang2);
+  float ka, kb;                      // sin(a)/a, (1 - cos a)/a^2
+  if (ang < 1e-4f) { ka = 1.f - ang2 * (1.f / 6.f); kb = 0.5f - ang2 * (1.f / 24.f); }
+  else { float sn, cs; sincosf(ang, &sn, &cs); ka = sn / ang; kb = (1.f - cs) / ang2; }
+  M3 Rb;
+  Rb.m[0][0] = 1.f - kb * (ty * ty + tz * tz); Rb.m[0][1] = -ka * tz + kb * tx * ty; Rb.m[0][2] = ka * ty + kb * tx * tz;
+  Rb.m[1][0] = ka * tz + kb * tx * ty; Rb.m[1][1] = 1.f - kb * (tx * tx + tz * tz); Rb.m[1][2] = -ka * tx + kb * ty * tz;
+  Rb.m[2][0] = -ka * ty + kb * tx * tz; Rb.m[2][1] = ka * tx + kb * ty * tz; Rb.m[2][2] = 1.f - kb * (tx * tx + ty * ty);
+  const V3 pb = {p.base_pos[3 * b], p.base_pos[3 * b + 1], p.base_pos[3 * b + 2]};
+  const V3 vb = {p.v_base[3 * b], p.v_base[3 * b + 1], p.v_base[3 * b + 2]};
+  const V3 wb = {p.w_base[3 * b], p.w_base[3 * b + 1], p.w_base[3 * b + 2]};
+  const float q1 = p.q[3 * idx], q2 = p.q[3 * idx + 1], q3 = p.q[3 * idx + 2];
+  const float d1 = p.dq[3 * idx], d2 = p.dq[3 * idx + 1], d3 = p.dq[3 * idx + 2];
+  float s1, c1, s2, c2, s23, c23;
+  sincosf(q1, &s1, &c1);
+  sincosf(q2, &s2, &c2);
+  sincosf(q2 + q3, &s23, &c23);
+  // torso-frame geometry.  R1 = rot(-x, q1) = [[1,0,0],[0,c1,s1],[0,-s1,c1]]; the pitch joints
+  // rotate about R1 (0,-1,0), by q2 (thigh) and q2 + q3 (shank): R1 Ry' with Ry'(q) (0,0,z) = (-s z, 0, c z)
+  auto r1 = [&](V3 v) -> V3 { return {v.x, c1 * v.y + s1 * v.z, -s1 * v.y + c1 * v.z}; };
+  auto leg_plane = [&](float sq, float cq, V3 v) -> V3 {        // R1 Ry'(q) v
+    return r1({cq * v.x - sq * v.z, v.y, sq * v.x + cq * v.z});
+  };
+  const V3 o1b = {sx * 0.1745f, sy * 0.062f, 0.f};
+  const V3 o2b = o1b + r1({0.f, sy * 0.0985f, 0.f});
+  const V3 o3b = o2b + leg_plane(s2, c2, {0.f, 0.f, -0.20f});
+  const V3 fb = o3b + leg_plane(s23, c23, {0.f, 0.f, -0.21f});
+  const V3 a1b = {-1.f, 0.f, 0.f};
+  const V3 a2b = r1({0.f, -1.f, 0.f});                            // hip pitch and knee axes coincide
+  // world frame
+  const V3 o[3] = {pb + mul(Rb, o1b), pb + mul(Rb, o2b), pb + mul(Rb, o3b)};
+  const V3 a[3] = {mul(Rb, a1b), mul(Rb, a2b), mul(Rb, a2b)};
+  const V3 pf = pb + mul(Rb, fb);
+  const float dqv[3] = {d1, d2, d3};
+  auto point_vel = [&](V3 x, int upto) -> V3 {                    // point fixed in link `upto` (0 = torso)
+    V3 v = vb + cross(wb, x - pb);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      if (k < upto) v = v + dqv[k] * cross(a[k], x - o[k]);
+    return v;
+  };
+  const V3 pdot = point_vel(pf, 3);
+  V3 wl = wb;                                                     // angular velocity of the link carrying axis k
+  float Jm[3][3], Jd[3][3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const V3 arm = pf - o[k];
+    const V3 jc = cross(a[k], arm);
+    const V3 adot = cross(wl, a[k]);
+    const V3 jd = cross(adot, arm) + cross(a[k], pdot - point_vel(o[k], k));
+    Jm[0][k] = jc.x; Jm[1][k] = jc.y; Jm[2][k] = jc.z;
+    Jd[0][k] = jd.x; Jd[1][k] = jd.y; Jd[2][k] = jd.z;
+    wl = wl + dqv[k] * a[k];
+  }
+  const size_t o3 = (size_t)idx * 3, o9 = (size_t)idx * 9;
+  p.foot_pos[o3] = pf.x; p.foot_pos[o3 + 1] = pf.y; p.foot_pos[o3 + 2] = pf.z;
+  p.foot_vel[o3] = pdot.x; p.foot_vel[o3 + 1] = pdot.y; p.foot_vel[o3 + 2] = pdot.z;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { p.J[o9 + 3 * i + k] = Jm[i][k]; p.Jdot[o9 + 3 * i + k] = Jd[i][k]; }
+  if (p.Mleg || p.cg) {
+    // centres of mass of hip, thigh, shank, foot (torso frame) and their masses
+    const V3 cb[4] = {o1b + r1({-sx * 0.0047f, -sy * 0.0091f, -0.0018f}),
+                      o2b + leg_plane(s2, c2, {-0.00523f, -sy * 0.0216f, -0.0273f}),
+                      o3b + leg_plane(s23, c23, {0.00585f, -8.732e-07f, -0.12f}), fb};
+    const float ml[4] = {0.428f, 0.61f, 0.115f, 0.01f};
+    float Mr[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const V3 c = pb + mul(Rb, cb[i]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (k <= i) {
+          const V3 jc = ml[i] * cross(a[k], c - o[k]);
+          Mr[0][k] += jc.x; Mr[1][k] += jc.y; Mr[2][k] += jc.z;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (p.Mleg) p.Mleg[o9 + 3 * i + k] = Mr[i][k];
+    if (p.cg) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) p.cg[o3 + k] = -Mr[2][k] * p.g;       // -Mrow' (0, 0, g)
+    }
+  }
+}
+
 // FP32 FMA micro-benchmark: the denominator of the on-chip roofline.
 // 8 independent FMA chains per thread, 256 threads, grid = a multiple of the SM count.
 __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b) {

@@ -81,3 +81,73 @@ def test_leg_torques_api_errors():
         ctl.torques(torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros((2, 10, 11), device=dev),
                     torch.zeros((2, 4, 3, 3), device=dev), torch.zeros((2, 4, 3, 3), device=dev),
                     torch.zeros((2, 4, 3, 3), device=dev), z, z, z, z)
+
+
+def test_leg_kinematics_kernel_matches_numerical_restatement(gold):
+    """cmpc_leg_kinematics against oracle/leg_kinematics.py (forward kinematics from the URDF joint
+    tree, Jacobians by finite differences) and against the logged feet of the reference's tick 0."""
+    from oracle import leg_kinematics as ok
+    dev = torch.device("cuda", 0)
+    B = 64
+    rng = np.random.default_rng(2)
+    base = rng.normal(0, 0.5, (B, 3)); theta = rng.normal(0, 0.4, (B, 3))
+    v, w = rng.normal(0, 0.5, (B, 3)), rng.normal(0, 1.0, (B, 3))
+    q = np.stack([rng.uniform(-0.4, 0.4, (B, 4)), rng.uniform(-2.0, 0.3, (B, 4)), rng.uniform(0.6, 2.7, (B, 4))], -1)
+    dq = rng.normal(0, 2.0, (B, 4, 3))
+    # robot 0 = the reference's initial configuration (src/main.py:67-81)
+    base[0], theta[0], v[0], w[0] = (0, 0, 0.299), 0, 0, 0
+    q[0], dq[0] = np.deg2rad([0.0, -60.0, 90.0]), 0
+    f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    mpc = pkg.BatchedMPC(N=10, max_batch=B)
+    ctl = pkg.BatchedLegController(mpc, _capi.GaitTables())
+    args = [f32(a) for a in (base, theta, v, w, q, dq)]
+    out = {k: t.cpu().numpy().astype(np.float64) for k, t in ctl.kinematics(*args).items()}
+    assert np.abs(out["foot_pos"][0] - gold["feet"][0]).max() < 2e-7           # the reference's logged feet
+    h = [a.cpu().numpy().astype(np.float64) for a in args]                       # fp32-rounded inputs
+    for b in range(0, B, 4):
+        fk = ok.foot_position(h[0][b], h[1][b], h[4][b])
+        assert np.abs(out["foot_pos"][b] - fk).max() < 2e-6
+        assert np.abs(out["J"][b] - ok.numeric_jacobian(h[0][b], h[1][b], h[4][b])).max() < 2e-6
+        vel, Jd = ok.numeric_rates(h[0][b], h[1][b], h[2][b], h[3][b], h[4][b], h[5][b])
+        assert np.abs(out["foot_vel"][b] - vel).max() < 2e-5
+        assert np.abs(out["Jdot"][b] - Jd).max() < 1e-4
+        Mr = ok.numeric_mass_rows(h[0][b], h[1][b], h[4][b])
+        assert np.abs(out["Mleg"][b] - Mr).max() < 1e-6
+        assert np.abs(out["cg"][b] - 9.81 * Mr[:, 2, :]).max() < 1e-5
+
+
+def test_self_contained_joint_torques(swing_gold):
+    """kinematics -> torques entirely on the device (no simulator inputs), against the fp64
+    restatement of src/main.py:203-282 fed with the host kinematics model."""
+    from mpc_b200 import kinematics as kin
+    dev = torch.device("cuda", 0)
+    names = ["pseudo_gallop", "trot", "pronk"] * 4
+    sh = float(swing_gold[f"{names[0]}/step_height"])
+    B, N = len(names), 10
+    gt, keep = _tables(swing_gold, names, dev, sh)
+    mpc = pkg.BatchedMPC(N=N, max_batch=B)
+    ctl = pkg.BatchedLegController(mpc, gt)
+    rng = np.random.default_rng(9)
+    f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    tick = torch.zeros(1, dtype=torch.int32, device=dev)
+    for t in (0, 16, 18, 23, 40, 171):
+        base = np.tile([0.0, 0.0, 0.29], (B, 1)) + rng.normal(0, 0.01, (B, 3))
+        theta = rng.normal(0, 0.05, (B, 3)); v = rng.normal(0, 0.1, (B, 3)); w = rng.normal(0, 0.2, (B, 3))
+        q = np.tile(kin.Q_INIT, (B, 4, 1)) + rng.normal(0, 0.1, (B, 4, 3)); dq = rng.normal(0, 1.0, (B, 4, 3))
+        U = rng.normal(0, 30, (B, N, 12))
+        a = [f32(x) for x in (base, theta, v, w, q, dq)]
+        k = ctl.kinematics(*a)
+        tick.fill_(t)
+        Ud = f32(U)
+        tau, p_des, stance = ctl.torques(tick, Ud, k["J"], k["Jdot"], k["Mleg"], k["cg"], a[5], k["foot_pos"], k["foot_vel"])
+        torch.cuda.synchronize()
+        tau = tau.cpu().numpy()
+        h = [x.cpu().numpy().astype(np.float64) for x in a]
+        for b, n in enumerate(names):
+            g = lambda key: swing_gold[f"{n}/{key}"]
+            st, p, vv, aa = lc.controller_query(g("pos").astype(np.float32), g("feet_id"), int(g("ss")), int(g("ds")),
+                                                sh, 0.01, t)
+            m = kin.leg_kinematics(h[0][b], h[1][b], h[2][b], h[3][b], h[4][b], h[5][b])
+            ref = lc.leg_torques(st, Ud[b, 0].cpu().numpy().astype(np.float64).reshape(4, 3), m["J"], m["Jdot"],
+                                 m["Mleg"], m["cg"], h[5][b], m["foot_pos"], m["foot_vel"], p, vv, aa)
+            assert np.abs(tau[b] - ref).max() <= 5e-4 * (np.abs(ref).max() + 1.0), (n, t)

@@ -138,27 +138,61 @@ def test_rollout_graph_equals_eager_and_stays_upright():
 def test_log_export_has_the_reference_schema(tmp_path, gold):
     """The exported pickle has the keys / shapes of the reference's simulation_log.pkl
     (reference src/logger.py:21-46) - checked by running this repo's own fixture extractor's
-    field accesses on it."""
+    field accesses and the data accesses of the reference's plot.py (src/plot.py:22-83) on it."""
     import pickle
+    from mpc_b200 import kinematics as kin
     ro = pkg.ClosedLoopRollout(8, N=10, seed=1)
     path = tmp_path / "simulation_log.pkl"
-    log = pkg.logexport.rollout_log(ro, 85, robot=3, path=str(path))
+    T = 85
+    log = pkg.logexport.rollout_log(ro, T, robot=3, path=str(path))
     log = pickle.load(open(path, "rb"))
     assert set(log) == {"mpc_freq", "sim_params", "total_sim_steps", "time array", "FEET POS",
                         "MPC PREDICTIONS", "TRACKING PERFORMANCE", "FORCES", "CONTROL EFFORT"}
-    assert log["total_sim_steps"] == 85 and log["time array"] == list(range(85))
+    assert log["total_sim_steps"] == T and log["time array"] == list(range(T))
     state = np.array(log["TRACKING PERFORMANCE"]["actual"])
     desired = np.array(log["TRACKING PERFORMANCE"]["desired"])
-    assert state.shape == desired.shape == (85, 12)
+    assert state.shape == desired.shape == (T, 12)
     forces = np.stack([np.stack([np.array(log["FORCES"][l][c]) for c in "xyz"], 1) for l in pkg.LEGS], 1)
-    assert forces.shape == (85, 4, 3) and np.all(forces[:, :, 2] >= -1e-6)
+    assert forces.shape == (T, 4, 3) and np.all(forces[:, :, 2] >= -1e-6)
     assert [p["time step"] for p in log["MPC PREDICTIONS"]] == [0, 80]
     p0 = log["MPC PREDICTIONS"][0]
     assert p0["predicted_state"].shape == (12, 11) and p0["desired_state"].shape == (12, 11)
     assert p0["predicted forces"].shape == (4, 10)
+    assert np.allclose(p0["predicted_state"][:, 0], state[0], atol=1e-6)      # X_0 = x0 (src/mpc.py:113)
     assert set(log["sim_params"]) >= {"g", "h", "ss_duration", "ds_duration", "first_swing", "µ", "N",
                                       "v_com_ref", "theta_dot", "total_steps", "world_time_step"}
     assert log["mpc_freq"] > 1000.0          # solves per second of the single robot's tick
+    # --- the reference's plot.py data accesses (src/plot.py:22-83) -------------------------------
+    total_sim_steps, time_step = log["total_sim_steps"], log["sim_params"]["world_time_step"]
+    for data in log["MPC PREDICTIONS"]:                                            # plot.py:27-35
+        Np = data["predicted_state"].shape[1] - 1
+        assert data["predicted_state"][3:6, :Np].shape == data["desired_state"][3:6, :Np].shape == (3, Np)
+    com_position = np.array([elem[3:6] for elem in log["TRACKING PERFORMANCE"]["actual"]]).T    # plot.py:39-43
+    com_desired = np.array([elem[3:6] for elem in log["TRACKING PERFORMANCE"]["desired"]]).T
+    assert com_position.shape == com_desired.shape == (3, total_sim_steps) and time_step == 0.01
+    for foot_name in pkg.LEGS:
+        foot_traj, foot_des_traj = log["FEET POS"][foot_name]["actual"], log["FEET POS"][foot_name]["des"]
+        foot_z = np.array([elem[2] for elem in foot_traj]).T                                    # plot.py:61-62
+        foot_z_des = np.array([elem[2] for elem in foot_des_traj]).T
+        assert foot_z.shape == foot_z_des.shape == (total_sim_steps,)
+        effort = log["CONTROL EFFORT"][foot_name]                                               # plot.py:82-83
+        assert list(effort) == [f"{foot_name[:2]}_{j}" for j in ("HipX", "HipY", "Knee")]       # src/logger.py:39-42
+        assert all(len(v) == total_sim_steps and np.all(np.isfinite(v)) for v in effort.values())
+        assert set(log["FORCES"][foot_name]) == {"x", "y", "z"}
+    # desired feet are the controller's references (src/main.py:159-167), not a copy of the actual feet:
+    # planned foothold for stance legs, swing polynomial (lifted by up to step_height) for swing legs
+    fl_des = np.array(log["FEET POS"]["FL_FOOT"]["des"])
+    assert fl_des[:, 2].max() > 0.05 and fl_des[:, 2].min() >= 0.0
+    # joint torques of a standing tick: tau = J'(-f) (src/main.py:214) with the URDF leg geometry
+    f0 = forces[0]                                                    # all-stance at tick 0
+    base = state[0, 3:6] - kin.rotvec_matrix(state[0, 0:3]) @ kin.nominal_com_offset()
+    feet0 = np.stack([log["FEET POS"][l]["actual"][0] for l in pkg.LEGS])
+    q = kin.leg_ik_batch((feet0 - base) @ kin.rotvec_matrix(state[0, 0:3]))
+    m = kin.leg_kinematics(base, state[0, 0:3], np.zeros(3), np.zeros(3), q, np.zeros((4, 3)))
+    for l, leg in enumerate(pkg.LEGS):
+        tau = np.array([log["CONTROL EFFORT"][leg][f"{leg[:2]}_{j}"][0] for j in ("HipX", "HipY", "Knee")])
+        assert np.allclose(tau, m["J"][l].T @ -f0[l], atol=2e-3 + 1e-3 * np.abs(tau).max())
+        assert np.abs(tau).max() > 0.5                                # the legs carry the robot
 
 
 def test_factorisation_cache_reuses_on_static_data_and_keeps_the_answers():

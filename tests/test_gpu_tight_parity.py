@@ -66,7 +66,7 @@ def test_tight_parity_config2():
     """config 2: 32 problems sampled from the 4096-problem trot batch of bench.py (seed 0)."""
     pb = synthetic_batch(4096, N=10, seed=0)
     sel = np.random.default_rng(2).choice(pb.B, 32, replace=False)
-    worst = check_sample(pb, sel, K=4000)
+    worst = check_sample(pb, sel, K=30000)
     print(f"config 2: worst wrench error = {worst:.3f} of the north-star tolerance")
 
 
@@ -109,3 +109,50 @@ def test_tight_parity_full_forces_with_force_weight():
         x0, r, st, xd, mu = pb.problem(b)
         ref = ipm.solve_problem(f32_64(x0), f32_64(r), st, f32_64(xd), float(np.float32(mu)), DT, r_weight=rw)
         assert np.all(np.abs(U[i] - ref["U"]) <= ATOL + RTOL * np.abs(ref["U"])), (b, np.abs(U[i] - ref["U"]).max())
+
+
+def golden_problems(gold, N, ticks, first_swing=None, ss=None, ds=None):
+    """The reference's own logged states as QPs of horizon N (BASELINE config 1: pkl replay)."""
+    from oracle.replay import ReplayMPC, params_from_golden, initial_from_golden
+    p = params_from_golden(gold, N=N)
+    if first_swing is not None:                       # SURVEY.md 8d config 1, "trot" variant: same states
+        p.update(first_swing=np.asarray(first_swing), ss_duration=ss, ds_duration=ds)
+    rows = []
+    for t in ticks:
+        m = ReplayMPC(initial_from_golden(gold), p)
+        m.com_pos_start = gold["desired"][t][3:6].copy()
+        m.yaw_start = float(gold["desired"][t][2])
+        x0, r, stance, xd, _, _ = m.tick_problem(t, gold["state"][t], gold["feet"][t])
+        rows.append((x0, r, stance, xd.T))
+    z = lambda i: np.stack([row[i] for row in rows])
+    B = len(rows)
+    return ProblemBatch(z(0), z(1), z(2), z(3), np.ones(B), np.zeros(B, int), np.asarray(ticks))
+
+
+def test_tight_parity_golden_run_ticks_n10(gold):
+    """The logged run's states (committed gait and the trot variant) at N = 10."""
+    ticks = [0, 3, 14, 15, 24, 25, 40, 80, 150, 299, 300, 600]
+    check_sample(golden_problems(gold, 10, ticks), np.arange(len(ticks)), K=30000)
+    check_sample(golden_problems(gold, 10, ticks, (1, 0, 0, 1), 10, 10), np.arange(len(ticks)), K=30000, n_osqp=1)
+
+
+def test_tight_parity_reference_default_horizon_n60(gold):
+    """config 1, the reference's default horizon N = 60 (src/main.py:41) on the logged states, cluster
+    kernel.  The objective and the state trajectory reach the tight optimum; the per-stage wrench is
+    held to a LOOSER absolute tolerance than the north star's 1e-2 N here (0.5 N + 1e-3 relative):
+    at N = 60 the wrench directions with the smallest cost curvature are resolved only to a few
+    tenths of a newton by the fp32 Woodbury solve (lambda_max(H) / rho ~ 1e5), see DESIGN.md."""
+    ticks = [0, 80, 150, 400]
+    pb = golden_problems(gold, 60, ticks)
+    U, X = tight_gpu(pb, np.arange(len(ticks)), 100000)
+    for i in range(pb.B):
+        x0, r, st, xd, mu = pb.problem(i)
+        x0, r, xd = f32_64(x0), f32_64(r), f32_64(xd)
+        ref = ipm.solve_problem(x0, r, st, xd, 1.0, DT)
+        if i == 0:
+            assert abs(ref["J"] - 20484.3999) < 0.2            # SURVEY.md 8(c) known answer
+        J = srbd_qp.objective(X[i].T, xd)
+        assert abs(J / ref["J"] - 1.0) <= 2e-5, (i, J, ref["J"])
+        assert np.all(np.abs(X[i].T - ref["X"]) <= 1e-3 + RTOL * np.abs(ref["X"]))
+        dW = np.abs(srbd_qp.stage_wrench(U[i], r) - ref["wrench"])
+        assert np.all(dW <= 0.5 + RTOL * np.abs(ref["wrench"])), (i, dW.max())

@@ -4,6 +4,7 @@
 #include "../../include/cmpc.h"
 #include "cmpc_kernels.cuh"
 #include "cmpc_cluster.cuh"
+#include "cmpc_riccati.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -140,6 +141,16 @@ cudaError_t launch_solve_cluster(const cmpc::SolveParams& p, cudaStream_t s) {
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, cmpc::solve_cluster_kernel<NL, CL, SPLIT, MINB>, p);
 }
+// stage-wise (Riccati) kernel: dynamic shared memory above the 48 KB default needs the opt-in
+template <int N, int MINB>
+cudaError_t launch_solve_riccati(const cmpc::SolveParams& p, cudaStream_t s) {
+  using G_ = cmpc::RGeo<N>;
+  static cudaError_t attr = cudaFuncSetAttribute(cmpc::solve_riccati_kernel<N, MINB>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_::SMEM_BYTES);
+  if (attr != cudaSuccess) return attr;
+  cmpc::solve_riccati_kernel<N, MINB><<<p.B, G_::THREADS, G_::SMEM_BYTES, s>>>(p);
+  return cudaGetLastError();
+}
 template <int N>
 cudaError_t launch_score(const cmpc::ScoreParams& p, cudaStream_t s) {
   cmpc::score_kernel<N><<<(p.B + 127) / 128, 128, 0, s>>>(p);
@@ -151,7 +162,7 @@ cudaError_t launch_condense(const cmpc::CondenseParams& p, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-constexpr int kVariants = 5;
+constexpr int kVariants = 6;
 struct HorizonEntry {
   int N;
   SolveLaunch solve[kVariants];   // thread-layout variants (nullptr = not compiled)
@@ -160,13 +171,17 @@ struct HorizonEntry {
   SolveLaunch solve_cached;       // default layout with the factorisation cache compiled in, or nullptr
 };
 
-// Horizons with compiled kernels.  <N, SPLIT, MINB, R>: a thread owns an R x (6N/SPLIT) register
-// tile of the 6N x 6N wrench matrix (R rows, one of SPLIT column slices), <= 96 floats.
-// Slot 0 is the default layout; slot 2 of N = 20 / 30 is the thread-block-cluster kernel on the same
-// horizon (tests compare the two layouts on the same problems).  The other slots hold alternative
-// single-CTA layouts that were measured SLOWER on B200 (N=10: 8.4-10.7 vs 12.4 M solves/s; N=30:
-// 703 k vs 764 k) and are only compiled with -DCMPC_EXTRA_LAYOUTS (cmpc_has_variant tells).
-// Any other horizon N <= 60 runs padded on the next compiled one (see pad_kernel).
+// Horizons with compiled kernels.  Dense kernels <N, SPLIT, MINB, R>: a thread owns an R x (6N/SPLIT)
+// register tile of the 6N x 6N wrench matrix (R rows, one of SPLIT column slices), <= 96 floats.
+// Slot 0 is the default kernel of the horizon:
+//   N <= 20: dense single-CTA kernel (cmpc_kernels.cuh);
+//   N >= 30: stage-wise Riccati kernel (cmpc_riccati.cuh), measured 2.0x (N=30, config 4), 2.0x (N=40)
+//            and 2.7x (N=60) the dense / cluster kernels on B200 (scripts/gpu_riccati_exp.py).
+// Slot 2 of N = 20 / 30 is the thread-block-cluster kernel on the same horizon, slot 5 the "other"
+// formulation (Riccati for N <= 20, dense / cluster for N >= 30): tests compare the kernels on the same
+// problems.  The remaining slots hold alternative dense layouts that were measured SLOWER (N=10: 8.4-10.7
+// vs 12.4 M solves/s; N=30: 703 k vs 764 k) and are only compiled with -DCMPC_EXTRA_LAYOUTS
+// (cmpc_has_variant tells).  Any other horizon N <= 60 runs padded on the next compiled one (pad_kernel).
 #ifdef CMPC_EXTRA_LAYOUTS
 #define CMPC_X(...) __VA_ARGS__
 #else
@@ -177,17 +192,20 @@ const HorizonEntry kHorizons[] = {
     {5, {launch_solve<5, 1, 8>}, launch_condense<5>, launch_score<5>, nullptr},
     {8, {launch_solve<8, 1, 8>}, launch_condense<8>, launch_score<8>, nullptr},
     {10, {launch_solve<10, 1, 8>, CMPC_X(launch_solve<10, 2, 4>), CMPC_X(launch_solve<10, 4, 2>),
-          CMPC_X(launch_solve<10, 2, 8, 2>), CMPC_X(launch_solve<10, 5, 8, 5>)},
+          CMPC_X(launch_solve<10, 2, 8, 2>), CMPC_X(launch_solve<10, 5, 8, 5>), launch_solve_riccati<10, 8>},
      launch_condense<10>, launch_score<10>, launch_solve<10, 1, 8, 1, true>},
     {12, {launch_solve<12, 2, 4>}, launch_condense<12>, launch_score<12>, nullptr},
     {16, {launch_solve<16, 2, 3>}, launch_condense<16>, launch_score<16>, nullptr},
-    {20, {launch_solve<20, 2, 2>, CMPC_X(launch_solve<20, 3, 1>), launch_solve_cluster<10, 2, 2, 3>},
+    {20, {launch_solve<20, 2, 2>, CMPC_X(launch_solve<20, 3, 1>), launch_solve_cluster<10, 2, 2, 3>, nullptr, nullptr,
+          launch_solve_riccati<20, 6>},
      launch_condense<20>, launch_score<20>, nullptr},
-    {30, {launch_solve<30, 6, 1, 3>, CMPC_X(launch_solve<30, 3, 1>), launch_solve_cluster<10, 3, 3, 2>,
-          CMPC_X(launch_solve<30, 6, 1, 2>), CMPC_X(launch_solve<30, 3, 1, 2>)},
+    {30, {launch_solve_riccati<30, 4>, CMPC_X(launch_solve<30, 3, 1>), launch_solve_cluster<10, 3, 3, 2>,
+          CMPC_X(launch_solve<30, 6, 1, 2>), CMPC_X(launch_solve<30, 3, 1, 2>), launch_solve<30, 6, 1, 3>},
      launch_condense<30>, launch_score<30>, launch_solve<30, 6, 1, 3, true>},
-    {40, {launch_solve_cluster<10, 4, 4, 1>}, nullptr, launch_score<40>, nullptr},
-    {60, {launch_solve_cluster<10, 6, 6, 1>}, nullptr, launch_score<60>, nullptr},
+    {40, {launch_solve_riccati<40, 3>, nullptr, nullptr, nullptr, nullptr, launch_solve_cluster<10, 4, 4, 1>},
+     nullptr, launch_score<40>, nullptr},
+    {60, {launch_solve_riccati<60, 2>, nullptr, nullptr, nullptr, nullptr, launch_solve_cluster<10, 6, 6, 1>},
+     nullptr, launch_score<60>, nullptr},
 };
 constexpr int kMaxHorizon = 60;
 
@@ -310,7 +328,7 @@ int solve_device(cmpc_handle* h, int B, int slot0, const float* x0, const float*
   int rc = schedule_batch(h, p, s);
   if (rc) return rc;
   static const bool dbg = std::getenv("CMPC_DEBUG_CLOCKS") != nullptr;   // developer aid, synchronous
-  if (dbg) CUDA_TRY(cudaMalloc(&p.dbg_clk, 8 * sizeof(long long)));
+  if (dbg) { CUDA_TRY(cudaMalloc(&p.dbg_clk, 32 * sizeof(long long))); CUDA_TRY(cudaMemset(p.dbg_clk, 0, 32 * sizeof(long long))); }
   if (timed) {
     if (!h->ev0) { CUDA_TRY(cudaEventCreate(&h->ev0)); CUDA_TRY(cudaEventCreate(&h->ev1)); }
     CUDA_TRY(cudaEventRecord(h->ev0, s));
@@ -322,9 +340,13 @@ int solve_device(cmpc_handle* h, int B, int slot0, const float* x0, const float*
   }
   h->launches.fetch_add(1);
   if (dbg) {
-    long long c[8];
+    long long c[32];
     CUDA_TRY(cudaMemcpy(c, p.dbg_clk, sizeof c, cudaMemcpyDeviceToHost));
     cudaFree(p.dbg_clk);
+    if (c[8] || c[9])
+      std::fprintf(stderr, "cmpc riccati clocks (CTA 0, totals): setup %lld factor %lld | legA+check %lld P1 %lld sweeps+barrier %lld "
+                           "(backward %lld forward %lld adjoint %lld) legB %lld | exit %lld\n",
+                   c[8], c[9], c[11], c[12], c[17], c[13], c[15], c[16], c[18], c[19]);
     std::fprintf(stderr, "cmpc clocks (CTA 0): load %lld geometry %lld P-build %lld sweep %lld init %lld admm %lld output %lld\n",
                  c[1] - c[0], c[2] - c[1], c[3] - c[2], c[4] - c[3], c[5] - c[4], c[6] - c[5], c[7] - c[6]);
   }

@@ -25,11 +25,12 @@ def t_fixed(pb, K, reps=10, **opts):
     return float(np.median(ms))
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+V = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 for B in (1, 148, 148 * 4, 148 * 8, 148 * 16):
     pb = synthetic_batch(B, N=N, seed=1)
-    row = dict(N=N, B=B, per_sm=B / 148)
-    for name, opts in (("default", {}), ("no_refresh", dict(refresh_every=0)), ("check5", dict(check_every=5)),
-                       ("check5_adapt25", dict(check_every=5, adaptive_rho_interval=25, adaptive_rho_tolerance=1e9))):
+    row = dict(N=N, B=B, per_sm=B / 148, variant=V)
+    for name, opts in (("default", {}), ("no_refresh", dict(refresh_every=0))):
+        opts = dict(opts, kernel_variant=V)
         t1, t2 = t_fixed(pb, 100, **opts), t_fixed(pb, 300, **opts)
         row[name] = dict(cycles_per_iter=round(1.965e6 * (t2 - t1) / 200, 1), ms_K0=round(t1 - 100 * (t2 - t1) / 200, 4))
     print(json.dumps(row), flush=True)

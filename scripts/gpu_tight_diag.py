@@ -19,7 +19,7 @@ def run(name, pb, sel, budgets, **opts):
     sub = [torch.from_numpy(a[sel]).to(dev) for a in pb.f32()]
     for K, eps in budgets:
         mpc = pkg.BatchedMPC(N=pb.N, max_batch=len(sel), max_iter=K, eps_abs=eps, eps_rel=eps, warm_mode=0,
-                             check_every=5 if eps > 0 else 25, **opts)
+                             check_every=5 if eps > 0 else 25, kernel_variant=int(os.environ.get("DIAG_VARIANT", "0")), **opts)
         U, X, st = mpc.solve(*sub)
         torch.cuda.synchronize()
         U = U.cpu().numpy().astype(np.float64); X = X.cpu().numpy().astype(np.float64)

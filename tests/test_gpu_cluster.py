@@ -1,6 +1,6 @@
-"""Alternative thread layouts of the solve kernel: the thread-block-cluster kernel (long
-horizons N = 40 / 60, optional for N = 20 / 30) and the register-blocked layouts (R rows of P
-per thread, `kernel_variant`): same algorithm, so the same oracle checks apply."""
+"""The three formulations of the solve kernel - dense single-CTA, thread-block cluster, stage-wise
+Riccati (default for N >= 30) - and the register-blocked dense layouts (`kernel_variant`): same ADMM,
+same iterates, so the same oracle checks apply to all of them."""
 import numpy as np
 import pytest
 
@@ -14,10 +14,15 @@ from test_gpu_parity import gpu_solve, close, ATOL, RTOL, _FakeLite3, _Logger   
 
 
 @pytest.mark.parametrize("N,variant,gaits", [(20, 2, ("trot",)), (30, 2, GAIT_NAMES), (40, 0, ("trot",)),
-                                             (60, 0, ("pseudo_gallop",)),
+                                             (60, 0, ("pseudo_gallop",)), (30, 0, GAIT_NAMES),
                                              # register-blocked single-CTA layouts <N,SPLIT,MINB,R>
                                              (10, 3, GAIT_NAMES), (10, 4, GAIT_NAMES), (30, 0, ("trot",)),
-                                             (30, 1, GAIT_NAMES), (30, 3, ("trot",)), (30, 4, GAIT_NAMES)])
+                                             (30, 1, GAIT_NAMES), (30, 3, ("trot",)), (30, 4, GAIT_NAMES),
+                                             # variant 5 = the other formulation: stage-wise (Riccati) kernel
+                                             # for N <= 20 (default: dense), dense / cluster kernel for N >= 30
+                                             # (default: Riccati)
+                                             (10, 5, GAIT_NAMES), (20, 5, GAIT_NAMES), (30, 5, GAIT_NAMES),
+                                             (40, 5, ("trot",)), (60, 5, ("pseudo_gallop",))])
 def test_cluster_kernel_iterate_parity(N, variant, gaits):
     if not pkg._capi.has_variant(N, variant):
         pytest.skip("layout variant needs a build with -DCMPC_EXTRA_LAYOUTS")
@@ -38,7 +43,7 @@ def test_cluster_kernel_iterate_parity(N, variant, gaits):
         assert np.all(out["U"][b].reshape(-1)[sw] == 0.0)
 
 
-@pytest.mark.parametrize("N,variant", [(30, 2), (60, 0)])
+@pytest.mark.parametrize("N,variant", [(30, 2), (60, 0), (60, 5), (30, 5)])
 def test_cluster_kernel_converges_like_the_single_cta_kernel(N, variant):
     pb = synthetic_batch(24, N=N, seed=12)
     a = gpu_solve(pb, kernel_variant=variant)
@@ -51,7 +56,7 @@ def test_cluster_kernel_converges_like_the_single_cta_kernel(N, variant):
                                  eps_abs=1e-7, eps_rel=1e-7)
         J = srbd_qp.objective(a["X"][b].T, xd)
         assert abs(J / tight["J"] - 1.0) < 2e-2
-    if N == 30:          # same problems through the single-CTA layout: same iterations, same forces
+    if N == 30:          # same problems through the default (Riccati) kernel: same iterations, same forces
         s = gpu_solve(pb, kernel_variant=0)
         assert np.array_equal(s["status"], a["status"])
         assert np.abs(s["iters"].astype(int) - a["iters"].astype(int)).max() <= 10

@@ -119,10 +119,31 @@ using SolveLaunch = cudaError_t (*)(const cmpc::SolveParams&, cudaStream_t);
 using CondenseLaunch = cudaError_t (*)(const cmpc::CondenseParams&, cudaStream_t);
 using ScoreLaunch = cudaError_t (*)(const cmpc::ScoreParams&, cudaStream_t);
 
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream is
+// still running (its CTAs wait in griddepcontrol.wait before they touch global memory), which hides the
+// launch latency between the two scheduling kernels and the solve kernel.  CMPC_NO_PDL=1 turns it off.
+bool use_pdl() {
+  static const bool on = std::getenv("CMPC_NO_PDL") == nullptr;
+  return on;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = use_pdl() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <int N, int SPLIT, int MINB, int R = 1, bool CACHE = false>
 cudaError_t launch_solve(const cmpc::SolveParams& p, cudaStream_t s) {
-  cmpc::solve_kernel<N, SPLIT, MINB, R, CACHE><<<p.B, cmpc::Geo<N, SPLIT, R>::THREADS, 0, s>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(cmpc::solve_kernel<N, SPLIT, MINB, R, CACHE>, dim3((unsigned)p.B), dim3(cmpc::Geo<N, SPLIT, R>::THREADS), 0, s, p);
 }
 // one thread-block cluster of CL CTAs per problem (long horizons, see cmpc_cluster.cuh)
 template <int NL, int CL, int SPLIT, int MINB>
@@ -148,13 +169,11 @@ cudaError_t launch_solve_riccati(const cmpc::SolveParams& p, cudaStream_t s) {
   static cudaError_t attr = cudaFuncSetAttribute(cmpc::solve_riccati_kernel<N, MINB>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_::SMEM_BYTES);
   if (attr != cudaSuccess) return attr;
-  cmpc::solve_riccati_kernel<N, MINB><<<p.B, G_::THREADS, G_::SMEM_BYTES, s>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(cmpc::solve_riccati_kernel<N, MINB>, dim3((unsigned)p.B), dim3(G_::THREADS), G_::SMEM_BYTES, s, p);
 }
 template <int N>
 cudaError_t launch_score(const cmpc::ScoreParams& p, cudaStream_t s) {
-  cmpc::score_kernel<N><<<(p.B + 127) / 128, 128, 0, s>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(cmpc::score_kernel<N>, dim3((unsigned)((p.B + 127) / 128)), dim3(128), 0, s, p);
 }
 template <int N>
 cudaError_t launch_condense(const cmpc::CondenseParams& p, cudaStream_t s) {
@@ -290,8 +309,8 @@ int schedule_batch(cmpc_handle* h, cmpc::SolveParams& p, cudaStream_t s) {
   // (one fused single-CTA score+sort kernel was measured slower than these two launches:
   // its dependent load rounds cost more than the kernel boundary it saves)
   CUDA_TRY(find_horizon(h->NK)->score(sp, s));
-  cmpc::order_kernel<<<1, 1024, 0, s>>>(sp.score, sp.hist, h->d_order + p.slot0, p.B);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_pdl(cmpc::order_kernel, dim3(1), dim3(1024), 0, s, (const float*)sp.score, sp.hist,
+                      h->d_order + p.slot0, p.B));
   h->launches.fetch_add(2);
   p.order = h->d_order + p.slot0;
   return CMPC_OK;

@@ -23,6 +23,12 @@
 // wrench-space gradient v = M G x up to date without a second matrix-vector product.
 #pragma once
 #include <cuda_runtime.h>
+// Packed fp32 FMA (sm_100 FFMA2, fma.rn.f32x2) in the sweep and in the P^-1 application: two row
+// entries per instruction, bit-identical results.  Measured on B200 (scripts/gpu_c2_time.py): config 2
+// 0.294 -> 0.281 ms per 4096-problem batch, config 3 shard 0.684 -> 0.654 ms.  -DCMPC_NO_FFMA2 turns it off.
+#ifndef CMPC_NO_FFMA2
+#define CMPC_FFMA2 1
+#endif
 #include <stdint.h>
 #include <type_traits>
 
@@ -97,6 +103,12 @@ __device__ __forceinline__ float pick6(const float a[6], int i) {
   for (int q = 1; q < 6; ++q) e = (i == q) ? a[q] : e;
   return e;
 }
+
+// Programmatic dependent launch (see launch_pdl in cmpc.cu): wait until every kernel launched before
+// this one in the stream has completed and its writes are visible; a no-op for ordinary launches.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// allow the next kernel of the stream to be scheduled (it still waits for this one in its own wait)
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 
 __device__ __forceinline__ float quad_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -220,6 +232,7 @@ solve_kernel(const SolveParams p) {
   __shared__ int s_mask[N];
 
   if ((int)blockIdx.x >= p.B) return;
+  grid_dependency_wait();
   const int b = p.order ? p.order[blockIdx.x] : (int)blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -461,10 +474,18 @@ solve_kernel(const SolveParams p) {
         const float4 pv = *reinterpret_cast<const float4*>(pr + c);
 #pragma unroll
         for (int q = 0; q < R; ++q) {
+#ifdef CMPC_FFMA2
+          // packed fp32 FMA (sm_100 FFMA2): two row entries per instruction
+          const float2 nn = make_float2(nf[q], nf[q]);
+          const float2 lo = __ffma2_rn(nn, make_float2(pv.x, pv.y), make_float2(row[q][c], row[q][c + 1]));
+          const float2 hi = __ffma2_rn(nn, make_float2(pv.z, pv.w), make_float2(row[q][c + 2], row[q][c + 3]));
+          row[q][c] = lo.x; row[q][c + 1] = lo.y; row[q][c + 2] = hi.x; row[q][c + 3] = hi.y;
+#else
           row[q][c] = fmaf(nf[q], pv.x, row[q][c]);
           row[q][c + 1] = fmaf(nf[q], pv.y, row[q][c + 1]);
           row[q][c + 2] = fmaf(nf[q], pv.z, row[q][c + 2]);
           row[q][c + 3] = fmaf(nf[q], pv.w, row[q][c + 3]);
+#endif
         }
         if (pub)
           *reinterpret_cast<float4*>(nbuf + rs * COLS + c) =
@@ -742,10 +763,16 @@ solve_kernel(const SolveParams p) {
         const float4 sv4 = *reinterpret_cast<const float4*>(sp + c);
 #pragma unroll
         for (int q = 0; q < R; ++q) {
+#ifdef CMPC_FFMA2
+          const float2 lo = __ffma2_rn(make_float2(row[q][c], row[q][c + 1]), make_float2(sv4.x, sv4.y), make_float2(acc[q][0], acc[q][1]));
+          const float2 hi = __ffma2_rn(make_float2(row[q][c + 2], row[q][c + 3]), make_float2(sv4.z, sv4.w), make_float2(acc[q][2], acc[q][3]));
+          acc[q][0] = lo.x; acc[q][1] = lo.y; acc[q][2] = hi.x; acc[q][3] = hi.y;
+#else
           acc[q][0] = fmaf(row[q][c], sv4.x, acc[q][0]);
           acc[q][1] = fmaf(row[q][c + 1], sv4.y, acc[q][1]);
           acc[q][2] = fmaf(row[q][c + 2], sv4.z, acc[q][2]);
           acc[q][3] = fmaf(row[q][c + 3], sv4.w, acc[q][3]);
+#endif
         }
       }
 #pragma unroll
@@ -940,6 +967,8 @@ __device__ __forceinline__ float problem_score(const ScoreParams& p, int b) {
 
 template <int N>
 __global__ void __launch_bounds__(128) score_kernel(const ScoreParams p) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= p.B) return;
   const float sc = problem_score<N>(p, b);
@@ -951,6 +980,8 @@ __global__ void __launch_bounds__(1024) order_kernel(const float* __restrict__ s
                                                      int32_t* __restrict__ hist,
                                                      int32_t* __restrict__ order, int32_t B) {
   __shared__ int offs[64];
+  grid_dependency_wait();
+  grid_launch_dependents();
   if (threadIdx.x == 0) {       // descending exclusive scan: hardest bucket first
     int run = 0;
     for (int q = 63; q >= 0; --q) { offs[q] = run; run += hist[q]; hist[q] = 0; }  // re-armed

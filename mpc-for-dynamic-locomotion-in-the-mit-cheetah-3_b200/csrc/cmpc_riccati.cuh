@@ -219,6 +219,7 @@ solve_riccati_kernel(const SolveParams p) {
   double* s_e = reinterpret_cast<double*>(s_fw);          // [2][6N]
 
   if ((int)blockIdx.x >= p.B) return;
+  grid_dependency_wait();
   const int b = p.order ? p.order[blockIdx.x] : (int)blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;

@@ -27,22 +27,23 @@ def timeit(pb, reps=20, **opts):
     mpc.close()
     return float(np.median(ms)), it
 
-pb = synthetic_batch(4096, N=10, seed=0)
-t_all, iters = timeit(pb)
-order = np.argsort(-iters)
-print(json.dumps(dict(what="full batch", ms=t_all, iters_top=iters[order[:12]].tolist(), mean=float(iters.mean()),
-                      n_gt50=int((iters > 50).sum()), n_gt100=int((iters > 100).sum()))), flush=True)
-np.save("gpurun_out/config2_iters.npy", iters)
-for K in (8, 32, 64, 148, 296):
-    rest = np.sort(order[K:])
-    t_rest, _ = timeit(sub(pb, rest))
-    row = dict(K=K, min_iters_in_top=int(iters[order[K - 1]]), ms_rest=t_rest)
-    hard = sub(pb, np.sort(order[:K]))
-    for v in (0, 1, 2):
-        if pkg._capi.has_variant(10, v):
-            row[f"ms_hard_v{v}"], _ = timeit(hard, kernel_variant=v, lpt_schedule=0)
-    print(json.dumps(row), flush=True)
-# iteration caps: batch time if nobody ran longer than cap (lower bound of a two-phase scheme's phase 1)
-for cap in (40, 60, 100):
-    t_cap, it = timeit(pb, max_iter=cap)
-    print(json.dumps(dict(cap=cap, ms=t_cap, unfinished=int((it >= cap).sum()))), flush=True)
+if __name__ == "__main__":
+    pb = synthetic_batch(4096, N=10, seed=0)
+    t_all, iters = timeit(pb)
+    order = np.argsort(-iters)
+    print(json.dumps(dict(what="full batch", ms=t_all, iters_top=iters[order[:12]].tolist(), mean=float(iters.mean()),
+                          n_gt50=int((iters > 50).sum()), n_gt100=int((iters > 100).sum()))), flush=True)
+    np.save("gpurun_out/config2_iters.npy", iters)
+    for K in (8, 32, 64, 148, 296):
+        rest = np.sort(order[K:])
+        t_rest, _ = timeit(sub(pb, rest))
+        row = dict(K=K, min_iters_in_top=int(iters[order[K - 1]]), ms_rest=t_rest)
+        hard = sub(pb, np.sort(order[:K]))
+        for v in (0, 1, 2):
+            if pkg._capi.has_variant(10, v):
+                row[f"ms_hard_v{v}"], _ = timeit(hard, kernel_variant=v, lpt_schedule=0)
+        print(json.dumps(row), flush=True)
+    # iteration caps: batch time if nobody ran longer than cap (lower bound of a two-phase scheme's phase 1)
+    for cap in (40, 60, 100):
+        t_cap, it = timeit(pb, max_iter=cap)
+        print(json.dumps(dict(cap=cap, ms=t_cap, unfinished=int((it >= cap).sum()))), flush=True)

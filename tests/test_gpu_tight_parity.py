@@ -66,7 +66,7 @@ def test_tight_parity_config2():
     """config 2: 32 problems sampled from the 4096-problem trot batch of bench.py (seed 0)."""
     pb = synthetic_batch(4096, N=10, seed=0)
     sel = np.random.default_rng(2).choice(pb.B, 32, replace=False)
-    worst = check_sample(pb, sel, K=30000)
+    worst = check_sample(pb, sel, K=100000)
     print(f"config 2: worst wrench error = {worst:.3f} of the north-star tolerance")
 
 
@@ -137,22 +137,17 @@ def test_tight_parity_golden_run_ticks_n10(gold):
 
 
 def test_tight_parity_reference_default_horizon_n60(gold):
-    """config 1, the reference's default horizon N = 60 (src/main.py:41) on the logged states, cluster
-    kernel.  The objective and the state trajectory reach the tight optimum; the per-stage wrench is
-    held to a LOOSER absolute tolerance than the north star's 1e-2 N here (0.5 N + 1e-3 relative):
-    at N = 60 the wrench directions with the smallest cost curvature are resolved only to a few
-    tenths of a newton by the fp32 Woodbury solve (lambda_max(H) / rho ~ 1e5), see DESIGN.md."""
+    """config 1, the reference's default horizon N = 60 (src/main.py:41) on the logged states and on
+    synthetic gallop / trot problems, stage-wise (Riccati) kernel: north-star tolerance on the per-stage
+    wrench, X and J.  ADMM converges slowly along the wrench directions with the smallest cost curvature at
+    this horizon (measured: worst problem at 9x the tolerance after 1e5 iterations, 3x after 3e5, 0.6x after
+    1e6, scripts/gpu_tight_diag.py), hence the budget of 10^6 iterations (~10 s of GPU time for the batch)."""
     ticks = [0, 80, 150, 400]
     pb = golden_problems(gold, 60, ticks)
-    U, X = tight_gpu(pb, np.arange(len(ticks)), 100000)
-    for i in range(pb.B):
-        x0, r, st, xd, mu = pb.problem(i)
-        x0, r, xd = f32_64(x0), f32_64(r), f32_64(xd)
-        ref = ipm.solve_problem(x0, r, st, xd, 1.0, DT)
-        if i == 0:
-            assert abs(ref["J"] - 20484.3999) < 0.2            # SURVEY.md 8(c) known answer
-        J = srbd_qp.objective(X[i].T, xd)
-        assert abs(J / ref["J"] - 1.0) <= 2e-5, (i, J, ref["J"])
-        assert np.all(np.abs(X[i].T - ref["X"]) <= 1e-3 + RTOL * np.abs(ref["X"]))
-        dW = np.abs(srbd_qp.stage_wrench(U[i], r) - ref["wrench"])
-        assert np.all(dW <= 0.5 + RTOL * np.abs(ref["wrench"])), (i, dW.max())
+    x0, r, st, xd, mu = pb.problem(0)
+    ref0 = ipm.solve_problem(f32_64(x0), f32_64(r), st, f32_64(xd), 1.0, DT)
+    assert abs(ref0["J"] - 20484.3999) < 0.2                  # SURVEY.md 8(c) known answer of tick 0
+    worst = check_sample(pb, np.arange(len(ticks)), K=1000000, n_osqp=0)
+    pb2 = synthetic_batch(64, N=60, gaits=("pseudo_gallop", "trot"), seed=0)
+    worst = max(worst, check_sample(pb2, np.arange(4), K=1000000, n_osqp=0))
+    print(f"N = 60: worst wrench error = {worst:.3f} of the north-star tolerance")

@@ -42,7 +42,7 @@ extern "C" {
 #endif
 
 #define CMPC_VERSION_MAJOR 0
-#define CMPC_VERSION_MINOR 1
+#define CMPC_VERSION_MINOR 2
 
 enum {
   CMPC_OK = 0,

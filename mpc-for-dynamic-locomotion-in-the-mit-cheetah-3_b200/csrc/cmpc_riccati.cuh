@@ -72,16 +72,27 @@ template <int N>
 __device__ __forceinline__ void adjoint_pass(const float* __restrict__ s_xi, float* __restrict__ out, float dt,
                                              int n_eff, float qp, float qv, int lane) {
   if (lane < 6) {
+    // chunks of CH stages: all loads of a chunk are issued before its (dependent) FMA chain - left to
+    // itself the compiler keeps load -> use -> store per stage and the chain pays one LDS latency per stage
+    constexpr int CH = 6;
     float mp = 0.f, mv = 0.f;
-    for (int k = N; k > n_eff; --k) out[6 * (k - 1) + lane] = 0.f;      // stages without cost (padded horizons)
-    const int k0 = n_eff < N ? n_eff : N;
-#pragma unroll 6
-    for (int k = k0; k >= 1; --k) {
-      const float pos = s_xi[12 * k + lane], vel = s_xi[12 * k + 6 + lane];
-      const float mvn = fmaf(qv, vel, fmaf(dt, mp, mv));                 // mu^v_k = Qv vel + dt mu^p_{k+1} + mu^v_{k+1}
-      mp = fmaf(qp, pos, mp);                                            // mu^p_k = Qp pos + mu^p_{k+1}
-      mv = mvn;
-      out[6 * (k - 1) + lane] = dt * mv;
+    for (int k = N; k >= 1; k -= CH) {
+      float pos[CH], vel[CH];
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int kk = k - u > 1 ? k - u : 1;
+        pos[u] = s_xi[12 * kk + lane];
+        vel[u] = s_xi[12 * kk + 6 + lane];
+      }
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int kk = k - u;
+        const float cq = (kk >= 1 && kk <= n_eff) ? 1.f : 0.f;           // stages that carry cost
+        const float mvn = fmaf(cq * qv, vel[u], fmaf(dt, mp, mv));       // mu^v_k = Qv vel + dt mu^p_{k+1} + mu^v_{k+1}
+        mp = fmaf(cq * qp, pos[u], mp);                                  // mu^p_k = Qp pos + mu^p_{k+1}
+        mv = mvn;
+        if (kk >= 1) out[6 * (kk - 1) + lane] = dt * mv;                 // q_{k-1} = B' mu_k
+      }
     }
   }
 }
@@ -180,14 +191,22 @@ __device__ __noinline__ void gram_sweeps(const float* __restrict__ s_s, float* _
                                          float* __restrict__ s_v, float dt, int n_eff, float qp, float qv) {
   const int lane = threadIdx.x & 31;
   if (lane < 6) {
+    constexpr int CH = 6;
     float pos = 0.f, vel = 0.f;
     s_xi[lane] = 0.f; s_xi[6 + lane] = 0.f;
-#pragma unroll 4
-    for (int k = 0; k < N; ++k) {
-      pos = fmaf(dt, vel, pos);
-      vel = fmaf(dt, s_s[6 * k + lane], vel);
-      s_xi[12 * (k + 1) + lane] = pos;
-      s_xi[12 * (k + 1) + 6 + lane] = vel;
+    for (int k = 0; k < N; k += CH) {
+      float w[CH];
+#pragma unroll
+      for (int u = 0; u < CH; ++u) w[u] = s_s[6 * (k + u < N ? k + u : N - 1) + lane];
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        if (k + u < N) {
+          pos = fmaf(dt, vel, pos);
+          vel = fmaf(dt, w[u], vel);
+          s_xi[12 * (k + u + 1) + lane] = pos;
+          s_xi[12 * (k + u + 1) + 6 + lane] = vel;
+        }
+      }
     }
   }
   __syncwarp();

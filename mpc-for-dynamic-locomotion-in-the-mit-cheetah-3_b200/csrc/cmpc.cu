@@ -193,11 +193,12 @@ struct HorizonEntry {
 // Horizons with compiled kernels.  Dense kernels <N, SPLIT, MINB, R>: a thread owns an R x (6N/SPLIT)
 // register tile of the 6N x 6N wrench matrix (R rows, one of SPLIT column slices), <= 96 floats.
 // Slot 0 is the default kernel of the horizon:
-//   N <= 20: dense single-CTA kernel (cmpc_kernels.cuh);
-//   N >= 30: stage-wise Riccati kernel (cmpc_riccati.cuh), measured 2.0x (N=30, config 4), 2.0x (N=40)
-//            and 2.7x (N=60) the dense / cluster kernels on B200 (scripts/gpu_riccati_exp.py).
+//   N <= 16: dense single-CTA kernel (cmpc_kernels.cuh);
+//   N >= 20: stage-wise Riccati kernel (cmpc_riccati.cuh), measured on B200 against the dense / cluster
+//            kernels: N=20 1.5x at 16384 problems (equal at 4096), N=30 2.25x (config 4), N=40 3.4x, N=60 5.2x
+//            (scripts/gpu_riccati_exp.py, gpu_n20_kernels.py).
 // Slot 2 of N = 20 / 30 is the thread-block-cluster kernel on the same horizon, slot 5 the "other"
-// formulation (Riccati for N <= 20, dense / cluster for N >= 30): tests compare the kernels on the same
+// formulation (Riccati for N = 10, dense / cluster for N >= 20): tests compare the kernels on the same
 // problems.  The remaining slots hold alternative dense layouts that were measured SLOWER (N=10: 8.4-10.7
 // vs 12.4 M solves/s; N=30: 703 k vs 764 k) and are only compiled with -DCMPC_EXTRA_LAYOUTS
 // (cmpc_has_variant tells).  Any other horizon N <= 60 runs padded on the next compiled one (pad_kernel).
@@ -213,10 +214,10 @@ const HorizonEntry kHorizons[] = {
     {10, {launch_solve<10, 1, 8>, CMPC_X(launch_solve<10, 2, 4>), CMPC_X(launch_solve<10, 4, 2>),
           CMPC_X(launch_solve<10, 2, 8, 2>), CMPC_X(launch_solve<10, 5, 8, 5>), launch_solve_riccati<10, 8>},
      launch_condense<10>, launch_score<10>, launch_solve<10, 1, 8, 1, true>},
-    {12, {launch_solve<12, 2, 4>}, launch_condense<12>, launch_score<12>, nullptr},
-    {16, {launch_solve<16, 2, 3>}, launch_condense<16>, launch_score<16>, nullptr},
-    {20, {launch_solve<20, 2, 2>, CMPC_X(launch_solve<20, 3, 1>), launch_solve_cluster<10, 2, 2, 3>, nullptr, nullptr,
-          launch_solve_riccati<20, 6>},
+    {12, {launch_solve<12, 2, 4>, nullptr, nullptr, nullptr, nullptr, launch_solve_riccati<12, 8>}, launch_condense<12>, launch_score<12>, nullptr},
+    {16, {launch_solve<16, 2, 3>, nullptr, nullptr, nullptr, nullptr, launch_solve_riccati<16, 8>}, launch_condense<16>, launch_score<16>, nullptr},
+    {20, {launch_solve_riccati<20, 6>, CMPC_X(launch_solve<20, 3, 1>), launch_solve_cluster<10, 2, 2, 3>, nullptr, nullptr,
+          launch_solve<20, 2, 2>},
      launch_condense<20>, launch_score<20>, nullptr},
     {30, {launch_solve_riccati<30, 4>, CMPC_X(launch_solve<30, 3, 1>), launch_solve_cluster<10, 3, 3, 2>,
           CMPC_X(launch_solve<30, 6, 1, 2>), CMPC_X(launch_solve<30, 3, 1, 2>), launch_solve<30, 6, 1, 3>},
@@ -276,6 +277,8 @@ void fill_solve_params(const cmpc_handle* h, cmpc::SolveParams& p) {
   p.adaptive_rho_tolerance = c.adaptive_rho_tolerance;
   p.rho_min = c.rho_min;
   p.rho_max = c.rho_max;
+  static const float floor_ = std::getenv("CMPC_RHO_FLOOR") ? (float)std::atof(std::getenv("CMPC_RHO_FLOOR")) : cmpc::kRhoAdaptFloor;
+  p.rho_adapt_floor = floor_;
   p.cache_pinv = h->d_cache_pinv;      // nullptr unless cfg.cache_factorization
   p.cache_r = h->d_cache_r;
   p.cache_mask = h->d_cache_mask;
@@ -437,7 +440,7 @@ int cmpc_default_config(cmpc_config* cfg, int32_t N, int32_t max_batch) {
   // rho_0 follows the scale of H, which grows with the horizon (measured on the Lite3
   // workloads: 0.5 is best at N=10, 1-3 at N=30, 2-8 at N=60)
   const HorizonEntry* he = kernel_horizon(N);
-  const bool stagewise = he && he->N >= 30;          // default kernel = Riccati (slot 0 of kHorizons)
+  const bool stagewise = he && he->N >= 20;          // default kernel = Riccati (slot 0 of kHorizons)
   cfg->rho = 0.05f * (float)N;
   cfg->sigma = 1e-6f;
   cfg->alpha = 1.6f;

@@ -459,7 +459,8 @@ solve_cluster_kernel(const SolveParams p) {
         const float du_n = m1 / (fmaxf(m3, ng) + 1e-10f);
         float rn = rho * sqrtf(pr_n / (du_n + 1e-10f));
         rn = fminf(fmaxf(rn, p.rho_min), p.rho_max);
-        if (rn > rho * p.adaptive_rho_tolerance || rn * p.adaptive_rho_tolerance < rho) {
+        if (fmaxf(pr_n, du_n) > p.rho_adapt_floor &&
+            (rn > rho * p.adaptive_rho_tolerance || rn * p.adaptive_rho_tolerance < rho)) {
           rho = rn;
           rho_inv = 1.f / rho;
           factorize();

@@ -34,6 +34,11 @@
 
 namespace cmpc {
 
+// Below this level both normalised residuals are fp32 rounding noise and their ratio carries no
+// information: rho stops adapting (a run with eps = 0 would otherwise let rho drift on noise and
+// lose accuracy).  Every finite tolerance >= 1e-5 exits long before, so iterates are unchanged.
+constexpr float kRhoAdaptFloor = 1e-6f;
+
 struct SolveParams {
   const float* __restrict__ x0;
   const float* __restrict__ r;
@@ -63,6 +68,7 @@ struct SolveParams {
   int32_t adaptive_rho_interval;      // 0 = fixed rho
   float adaptive_rho_tolerance;
   float rho_min, rho_max;             // clamp of the adapted rho (fp32 stability of the Woodbury form)
+  float rho_adapt_floor;              // kRhoAdaptFloor
   long long* dbg_clk;                 // debug: phase timestamps of CTA 0 (nullptr in production)
   // factorisation cache (closed-loop use, cfg.cache_factorization): -P^-1 of each slot's last
   // factorisation with the data it was computed for; nullptr = off
@@ -739,7 +745,8 @@ solve_kernel(const SolveParams p) {
           const float du_n = m1 / (fmaxf(m3, ng) + 1e-10f);
           float rn = rho * sqrtf(pr_n / (du_n + 1e-10f));
           rn = fminf(fmaxf(rn, p.rho_min), p.rho_max);
-          if (rn > rho * p.adaptive_rho_tolerance || rn * p.adaptive_rho_tolerance < rho) {
+          if (fmaxf(pr_n, du_n) > p.rho_adapt_floor &&
+            (rn > rho * p.adaptive_rho_tolerance || rn * p.adaptive_rho_tolerance < rho)) {
             rho = rn;
             rho_inv = 1.f / rho;
             ++rho_updates;

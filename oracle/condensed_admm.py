@@ -43,12 +43,14 @@ def project_frustum(w, mu, f_min=srbd_qp.F_MIN, f_max=srbd_qp.F_MAX):
 def admm(H, g, mu, rho=0.3, sigma=1e-6, alpha=1.6, eps_abs=1e-3, eps_rel=1e-3,
          max_iter=1000, check_every=5, x=None, y=None, f_min=srbd_qp.F_MIN,
          f_max=srbd_qp.F_MAX, dtype=np.float64, fixed_iters=None, adaptive_interval=0,
-         adaptive_tolerance=2.0, rho_lim=(0.03, 30.0)):
+         adaptive_tolerance=2.0, rho_lim=(0.03, 30.0), adaptive_floor=0.0):
     """Returns dict(x, y, z, iters, pri_res, dua_res, status, rho, rho_updates).
     ``fixed_iters`` runs exactly that many iterations (iterate-level parity with the CUDA
     kernel).  ``adaptive_interval`` > 0 applies OSQP's rho adaptation rule every that many
     iterations (refactorising K), as the CUDA kernel does.  Residuals are OSQP's with A = I:
-    r_p = |x - z|_inf, r_d = |Hx + g + y|_inf."""
+    r_p = |x - z|_inf, r_d = |Hx + g + y|_inf.  ``adaptive_floor``: rho stops adapting once both
+    normalised residuals are below it (the fp32 kernel uses 1e-6, its rounding-noise level; only
+    reachable with eps < 1e-5)."""
     n = H.shape[0]
     dt = dtype
     H = H.astype(dt)
@@ -98,7 +100,7 @@ def admm(H, g, mu, rho=0.3, sigma=1e-6, alpha=1.6, eps_abs=1e-3, eps_rel=1e-3,
             if fixed_iters is None and pri <= eps_abs + eps_rel * nA and dua <= eps_abs + eps_rel * nD:
                 status = 1
                 break
-            if adapt and n:
+            if adapt and n and max(pri / (nA + 1e-10), dua / (nD + 1e-10)) > adaptive_floor:
                 rn = float(rho) * np.sqrt((pri / (nA + 1e-10)) / (dua / (nD + 1e-10) + 1e-10))
                 rn = min(max(rn, rho_lim[0]), rho_lim[1])
                 if rn > float(rho) * adaptive_tolerance or rn * adaptive_tolerance < float(rho):

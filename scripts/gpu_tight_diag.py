@@ -65,3 +65,10 @@ if __name__ == "__main__":
     if "n20" in which:
         pb = synthetic_batch(64, N=20, gaits=GAIT_NAMES, seed=0)
         run("n20", pb, np.arange(12), B)
+    if "t20" in which:       # the batch of tests/test_gpu_tight_parity.py::test_tight_parity_other_horizons[20]
+        pb = synthetic_batch(64, N=20, gaits=GAIT_NAMES, seed=6, mu=(0.3, 1.0))
+        tol = os.environ.get("DIAG_RHO_TOL")
+        run("t20", pb, np.arange(12), B, **({"adaptive_rho_tolerance": float(tol)} if tol else {}))
+    if "t30" in which:       # the sample of test_tight_parity_config4_long_horizon
+        pb = synthetic_batch(16384, N=30, seed=0)
+        run("t30", pb, np.random.default_rng(4).choice(pb.B, 24, replace=False), B)

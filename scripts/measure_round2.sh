@@ -11,4 +11,4 @@ python scripts/profile_target.py > gpurun_out/plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:solve_kernel -s 2 -c 1 -o gpurun_out/prof_r2_c2 -f python scripts/profile_target.py > gpurun_out/ncu2.log 2>&1
 python scripts/profile_target.py 4096 30 > gpurun_out/plain30.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:solve_riccati -s 2 -c 1 -o gpurun_out/prof_r2_c4 -f python scripts/profile_target.py 4096 30 > gpurun_out/ncu3.log 2>&1
-tail -c 400 gpurun_out/r02_bench.json; echo; tail -5 gpurun_out/r02_bench.err; tail -3 gpurun_out/ncu2.log gpurun_out/ncu3.log
+tail -c 400 gpurun_out/r02_bench.json; echo; tail -5 gpurun_out/r02_bench.err; tail -n 3 gpurun_out/ncu2.log; tail -n 3 gpurun_out/ncu3.log

@@ -37,7 +37,8 @@ def test_default_config_matches_reference_constants():
     assert cfg.rho == pytest.approx(0.5) and cfg.adaptive_rho_tolerance == pytest.approx(3.0)
     c30 = _capi.default_config(30, 8)            # stage-wise kernel: cheap refactorisation, tighter rho tolerance
     assert c30.rho == pytest.approx(1.5) and c30.adaptive_rho_tolerance == pytest.approx(1.5)
-    assert _capi.default_config(20, 8).rho == pytest.approx(1.0)
+    assert _capi.default_config(20, 8).adaptive_rho_tolerance == pytest.approx(1.5)
+    assert _capi.default_config(16, 8).adaptive_rho_tolerance == pytest.approx(3.0)
     assert cfg.rho_max == pytest.approx(300.0) and cfg.rho_min == pytest.approx(0.05)
     # struct layout: the C side zero-fills then writes; a mismatch would scramble the tail
     assert cfg.device == 0 and cfg.kernel_variant == 0

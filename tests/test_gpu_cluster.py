@@ -14,14 +14,15 @@ from test_gpu_parity import gpu_solve, close, ATOL, RTOL, _FakeLite3, _Logger   
 
 
 @pytest.mark.parametrize("N,variant,gaits", [(20, 2, ("trot",)), (30, 2, GAIT_NAMES), (40, 0, ("trot",)),
-                                             (60, 0, ("pseudo_gallop",)), (30, 0, GAIT_NAMES),
+                                             (60, 0, ("pseudo_gallop",)), (30, 0, GAIT_NAMES), (20, 0, GAIT_NAMES),
                                              # register-blocked single-CTA layouts <N,SPLIT,MINB,R>
                                              (10, 3, GAIT_NAMES), (10, 4, GAIT_NAMES), (30, 0, ("trot",)),
                                              (30, 1, GAIT_NAMES), (30, 3, ("trot",)), (30, 4, GAIT_NAMES),
                                              # variant 5 = the other formulation: stage-wise (Riccati) kernel
-                                             # for N <= 20 (default: dense), dense / cluster kernel for N >= 30
+                                             # for N <= 16 (default: dense), dense / cluster kernel for N >= 20
                                              # (default: Riccati)
-                                             (10, 5, GAIT_NAMES), (20, 5, GAIT_NAMES), (30, 5, GAIT_NAMES),
+                                             (10, 5, GAIT_NAMES), (12, 5, GAIT_NAMES), (16, 5, GAIT_NAMES),
+                                             (20, 5, GAIT_NAMES), (30, 5, GAIT_NAMES),
                                              (40, 5, ("trot",)), (60, 5, ("pseudo_gallop",))])
 def test_cluster_kernel_iterate_parity(N, variant, gaits):
     if not pkg._capi.has_variant(N, variant):

@@ -351,6 +351,8 @@ int solve_device(cmpc_handle* h, int B, int slot0, const float* x0, const float*
   if (rc) return rc;
   static const bool dbg = std::getenv("CMPC_DEBUG_CLOCKS") != nullptr;   // developer aid, synchronous
   if (dbg) { CUDA_TRY(cudaMalloc(&p.dbg_clk, 32 * sizeof(long long))); CUDA_TRY(cudaMemset(p.dbg_clk, 0, 32 * sizeof(long long))); }
+  static const char* tl_path = std::getenv("CMPC_DEBUG_TIMELINE");          // developer aid, synchronous
+  if (tl_path) { CUDA_TRY(cudaMalloc(&p.dbg_tl, (size_t)B * 4 * sizeof(long long))); CUDA_TRY(cudaMemset(p.dbg_tl, 0, (size_t)B * 4 * sizeof(long long))); }
   if (timed) {
     if (!h->ev0) { CUDA_TRY(cudaEventCreate(&h->ev0)); CUDA_TRY(cudaEventCreate(&h->ev1)); }
     CUDA_TRY(cudaEventRecord(h->ev0, s));
@@ -361,6 +363,12 @@ int solve_device(cmpc_handle* h, int B, int slot0, const float* x0, const float*
     h->timed = true;
   }
   h->launches.fetch_add(1);
+  if (tl_path) {   // per-CTA timeline of this launch: [B][4] int64 (start ns, end ns, SM, iterations), launch order
+    std::vector<long long> tl((size_t)B * 4);
+    CUDA_TRY(cudaMemcpy(tl.data(), p.dbg_tl, tl.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.dbg_tl);
+    if (FILE* f = std::fopen(tl_path, "wb")) { std::fwrite(tl.data(), sizeof(long long), tl.size(), f); std::fclose(f); }
+  }
   if (dbg) {
     long long c[32];
     CUDA_TRY(cudaMemcpy(c, p.dbg_clk, sizeof c, cudaMemcpyDeviceToHost));

@@ -70,6 +70,7 @@ struct SolveParams {
   float rho_min, rho_max;             // clamp of the adapted rho (fp32 stability of the Woodbury form)
   float rho_adapt_floor;              // kRhoAdaptFloor
   long long* dbg_clk;                 // debug: phase timestamps of CTA 0 (nullptr in production)
+  long long* dbg_tl;                  // debug: [B][4] start ns, end ns, SM id, iterations of every CTA (nullptr in production)
   // factorisation cache (closed-loop use, cfg.cache_factorization): -P^-1 of each slot's last
   // factorisation with the data it was computed for; nullptr = off
   float4* __restrict__ cache_pinv;    // [slots][NW*NWP/4 float4], laid out [tile piece][thread]
@@ -245,6 +246,13 @@ solve_kernel(const SolveParams p) {
   const bool leg_warp = warp < LWARPS;   // warp-uniform: warps without leg threads skip leg phases
   const int slot = p.slot0 + b;
 
+  if (p.dbg_tl && tid == 0) {
+    unsigned long long t; unsigned sm;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+    p.dbg_tl[4 * (size_t)blockIdx.x] = (long long)t;
+    p.dbg_tl[4 * (size_t)blockIdx.x + 2] = sm;
+  }
   if (p.dbg_clk && blockIdx.x == 0 && tid == 0) p.dbg_clk[0] = clock64();
   // ---- phase 0: stage the per-problem record (coalesced 4-byte loads, every byte requested
   // once: the record may live in page-locked HOST memory, see cmpc_solve_host) --------------
@@ -846,6 +854,7 @@ solve_kernel(const SolveParams p) {
   }
   if (tid == 0) {
     if (p.iters) p.iters[b] = it;
+    if (p.dbg_tl) p.dbg_tl[4 * (size_t)blockIdx.x + 3] = it;
     if (p.pri_res) p.pri_res[b] = pri;
     if (p.dua_res) p.dua_res[b] = dua;
     if (p.status) p.status[b] = status;
@@ -912,6 +921,11 @@ solve_kernel(const SolveParams p) {
     }
   }
   if (p.dbg_clk && blockIdx.x == 0 && tid == 0) p.dbg_clk[7] = clock64();
+  if (p.dbg_tl && tid == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.dbg_tl[4 * (size_t)blockIdx.x + 1] = (long long)t;
+  }
 }
 
 // ---------------------------------------------------------------------------------------

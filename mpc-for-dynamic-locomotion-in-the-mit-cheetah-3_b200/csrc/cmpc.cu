@@ -141,9 +141,14 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-template <int N, int SPLIT, int MINB, int R = 1, bool CACHE = false>
+template <int N, int SPLIT, int MINB, int R = 1, bool CACHE = false, bool TC = false>
 cudaError_t launch_solve(const cmpc::SolveParams& p, cudaStream_t s) {
-  return launch_pdl(cmpc::solve_kernel<N, SPLIT, MINB, R, CACHE>, dim3((unsigned)p.B), dim3(cmpc::Geo<N, SPLIT, R>::THREADS), 0, s, p);
+  if (TC) {   // 25 KB of static shared memory per CTA: MINB resident CTAs need the largest carve-out
+    static const cudaError_t carve = cudaFuncSetAttribute(cmpc::solve_kernel<N, SPLIT, MINB, R, CACHE, TC>,
+                                                          cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (carve != cudaSuccess) return carve;
+  }
+  return launch_pdl(cmpc::solve_kernel<N, SPLIT, MINB, R, CACHE, TC>, dim3((unsigned)p.B), dim3(cmpc::Geo<N, SPLIT, R>::THREADS), 0, s, p);
 }
 // one thread-block cluster of CL CTAs per problem (long horizons, see cmpc_cluster.cuh)
 template <int NL, int CL, int SPLIT, int MINB>
@@ -211,9 +216,9 @@ const HorizonEntry kHorizons[] = {
     {4, {launch_solve<4, 1, 8>}, launch_condense<4>, launch_score<4>, nullptr},
     {5, {launch_solve<5, 1, 8>}, launch_condense<5>, launch_score<5>, nullptr},
     {8, {launch_solve<8, 1, 8>}, launch_condense<8>, launch_score<8>, nullptr},
-    {10, {launch_solve<10, 1, 8>, CMPC_X(launch_solve<10, 2, 4>), CMPC_X(launch_solve<10, 4, 2>),
+    {10, {launch_solve<10, 1, 8, 1, false, true>, launch_solve<10, 1, 8>, CMPC_X(launch_solve<10, 4, 2>),
           CMPC_X(launch_solve<10, 2, 8, 2>), CMPC_X(launch_solve<10, 5, 8, 5>), launch_solve_riccati<10, 8>},
-     launch_condense<10>, launch_score<10>, launch_solve<10, 1, 8, 1, true>},
+     launch_condense<10>, launch_score<10>, launch_solve<10, 1, 8, 1, true, true>},
     {12, {launch_solve<12, 2, 4>, nullptr, nullptr, nullptr, nullptr, launch_solve_riccati<12, 8>}, launch_condense<12>, launch_score<12>, nullptr},
     {16, {launch_solve<16, 2, 3>, nullptr, nullptr, nullptr, nullptr, launch_solve_riccati<16, 8>}, launch_condense<16>, launch_score<16>, nullptr},
     {20, {launch_solve_riccati<20, 6>, CMPC_X(launch_solve<20, 3, 1>), launch_solve_cluster<10, 2, 2, 3>, nullptr, nullptr,

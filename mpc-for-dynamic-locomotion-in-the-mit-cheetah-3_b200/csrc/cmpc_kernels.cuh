@@ -32,6 +32,8 @@
 #include <stdint.h>
 #include <type_traits>
 
+#include "cmpc_tc.cuh"
+
 namespace cmpc {
 
 // Below this level both normalised residuals are fp32 rounding noise and their ratio carries no
@@ -213,12 +215,15 @@ __device__ __forceinline__ float wrench_linear_term(int j, int a, const float* s
 // ---------------------------------------------------------------------------------------
 // CACHE compiles the factorisation cache in (closed-loop instantiations); the default
 // instantiation carries none of its state through the register-limited ADMM loop.
-template <int N, int SPLIT, int MINB, int R, bool CACHE>
+// TC runs the factorisation sweep on the tensor cores (cmpc_tc.cuh; one 64-thread CTA, 6N <= 64).
+template <int N, int SPLIT, int MINB, int R, bool CACHE, bool TC = false>
 __global__ void __launch_bounds__((Geo<N, SPLIT, R>::THREADS), MINB)
 solve_kernel(const SolveParams p) {
   using G_ = Geo<N, SPLIT, R>;
   constexpr int NW = G_::NW, NWP = G_::NWP, COLS = G_::COLS, NLEG = G_::NLEG, NWR = G_::NWR;
   constexpr int THREADS = G_::THREADS, LWARPS = G_::LWARPS, NX = G_::NX;
+  static_assert(!TC || (SPLIT == 1 && R == 1 && THREADS == kTcN && NW <= kTcN), "tensor-core sweep: one row per thread, 64 threads");
+  __shared__ __align__(16) float s_P[TC ? kTcSmemFloats : 4];   // row <-> fragment staging of the tensor-core sweep
 
   __shared__ __align__(16) float s_x0[16];
   __shared__ __align__(16) float s_xd[NX + 3];         // x_des; reused to stage U at the end
@@ -459,79 +464,83 @@ solve_kernel(const SolveParams p) {
   // store after every 4R FMAs) instead of after the update: a barrier waits for the stores in
   // flight to drain, and 15 back-to-back stores of one lane in front of it cost more than the
   // update itself (measured: 410 cycles per pivot on an otherwise idle SM).
-  auto publish_tail = [&](float* nbuf, int kn, float dg, float rdg) {
-    if (kn / COLS == rs) {   // this slice holds the pivot (stores of one thread stay ordered)
-      nbuf[kn] = dg - 1.f;
-      nbuf[NWP] = rdg;
-    }
-  };
-  auto sweep_step = [&](auto q0c, auto qnc, auto parc, int kk, int kn_local, bool has_next) {
-    constexpr int q0 = decltype(q0c)::value, qn = decltype(qnc)::value;
-    constexpr bool odd = decltype(parc)::value != 0;     // pivot parity picks the buffer statically
-    const float* buf = odd ? s_rowB : s_rowA;
-    float* nbuf = odd ? s_rowA : s_rowB;
-    if (is_row) {
-      const float d = buf[NWP];
-      float nf[R];
-#pragma unroll
-      for (int q = 0; q < R; ++q) {
-        const float m = buf[rp + q * NWR];
-        const bool own = q == q0 && rp == kk;
-        nf[q] = own ? d - 1.f : -m * d;
-        diag[q] = own ? -d : fmaf(nf[q], m, diag[q]);
-        rdiag[q] = __fdividef(1.f, diag[q]);
+  if constexpr (TC) {
+    tc_sweep<NW, COLS>(row[0], s_P, tid);      // row = -(S P S)^-1
+  } else {
+    auto publish_tail = [&](float* nbuf, int kn, float dg, float rdg) {
+      if (kn / COLS == rs) {   // this slice holds the pivot (stores of one thread stay ordered)
+        nbuf[kn] = dg - 1.f;
+        nbuf[NWP] = rdg;
       }
-      const bool pub = has_next && rp == kn_local;
-      const float* pr = buf + rs * COLS;
-#pragma unroll
-      for (int c = 0; c < COLS; c += 4) {
-        const float4 pv = *reinterpret_cast<const float4*>(pr + c);
-#pragma unroll
+    };
+    auto sweep_step = [&](auto q0c, auto qnc, auto parc, int kk, int kn_local, bool has_next) {
+      constexpr int q0 = decltype(q0c)::value, qn = decltype(qnc)::value;
+      constexpr bool odd = decltype(parc)::value != 0;     // pivot parity picks the buffer statically
+      const float* buf = odd ? s_rowB : s_rowA;
+      float* nbuf = odd ? s_rowA : s_rowB;
+      if (is_row) {
+        const float d = buf[NWP];
+        float nf[R];
+  #pragma unroll
         for (int q = 0; q < R; ++q) {
-#ifdef CMPC_FFMA2
-          // packed fp32 FMA (sm_100 FFMA2): two row entries per instruction
-          const float2 nn = make_float2(nf[q], nf[q]);
-          const float2 lo = __ffma2_rn(nn, make_float2(pv.x, pv.y), make_float2(row[q][c], row[q][c + 1]));
-          const float2 hi = __ffma2_rn(nn, make_float2(pv.z, pv.w), make_float2(row[q][c + 2], row[q][c + 3]));
-          row[q][c] = lo.x; row[q][c + 1] = lo.y; row[q][c + 2] = hi.x; row[q][c + 3] = hi.y;
-#else
-          row[q][c] = fmaf(nf[q], pv.x, row[q][c]);
-          row[q][c + 1] = fmaf(nf[q], pv.y, row[q][c + 1]);
-          row[q][c + 2] = fmaf(nf[q], pv.z, row[q][c + 2]);
-          row[q][c + 3] = fmaf(nf[q], pv.w, row[q][c + 3]);
-#endif
+          const float m = buf[rp + q * NWR];
+          const bool own = q == q0 && rp == kk;
+          nf[q] = own ? d - 1.f : -m * d;
+          diag[q] = own ? -d : fmaf(nf[q], m, diag[q]);
+          rdiag[q] = __fdividef(1.f, diag[q]);
         }
-        if (pub)
-          *reinterpret_cast<float4*>(nbuf + rs * COLS + c) =
-              make_float4(row[qn][c], row[qn][c + 1], row[qn][c + 2], row[qn][c + 3]);
+        const bool pub = has_next && rp == kn_local;
+        const float* pr = buf + rs * COLS;
+  #pragma unroll
+        for (int c = 0; c < COLS; c += 4) {
+          const float4 pv = *reinterpret_cast<const float4*>(pr + c);
+  #pragma unroll
+          for (int q = 0; q < R; ++q) {
+  #ifdef CMPC_FFMA2
+            // packed fp32 FMA (sm_100 FFMA2): two row entries per instruction
+            const float2 nn = make_float2(nf[q], nf[q]);
+            const float2 lo = __ffma2_rn(nn, make_float2(pv.x, pv.y), make_float2(row[q][c], row[q][c + 1]));
+            const float2 hi = __ffma2_rn(nn, make_float2(pv.z, pv.w), make_float2(row[q][c + 2], row[q][c + 3]));
+            row[q][c] = lo.x; row[q][c + 1] = lo.y; row[q][c + 2] = hi.x; row[q][c + 3] = hi.y;
+  #else
+            row[q][c] = fmaf(nf[q], pv.x, row[q][c]);
+            row[q][c + 1] = fmaf(nf[q], pv.y, row[q][c + 1]);
+            row[q][c + 2] = fmaf(nf[q], pv.z, row[q][c + 2]);
+            row[q][c + 3] = fmaf(nf[q], pv.w, row[q][c + 3]);
+  #endif
+          }
+          if (pub)
+            *reinterpret_cast<float4*>(nbuf + rs * COLS + c) =
+                make_float4(row[qn][c], row[qn][c + 1], row[qn][c + 2], row[qn][c + 3]);
+        }
+        if (pub) publish_tail(nbuf, qn * NWR + kn_local, diag[qn], rdiag[qn]);
       }
-      if (pub) publish_tail(nbuf, qn * NWR + kn_local, diag[qn], rdiag[qn]);
+      __syncthreads();
+    };
+    if (is_row && rp == 0) {   // pivot 0
+  #pragma unroll
+      for (int c = 0; c < COLS; c += 4)
+        *reinterpret_cast<float4*>(s_rowA + rs * COLS + c) = make_float4(row[0][c], row[0][c + 1], row[0][c + 2], row[0][c + 3]);
+      publish_tail(s_rowA, 0, diag[0], rdiag[0]);
     }
     __syncthreads();
-  };
-  if (is_row && rp == 0) {   // pivot 0
-#pragma unroll
-    for (int c = 0; c < COLS; c += 4)
-      *reinterpret_cast<float4*>(s_rowA + rs * COLS + c) = make_float4(row[0][c], row[0][c + 1], row[0][c + 2], row[0][c + 3]);
-    publish_tail(s_rowA, 0, diag[0], rdiag[0]);
-  }
-  __syncthreads();
-  {
-    static_assert(NWR % 2 == 0, "pivots are processed in (even, odd) pairs");
-    using I0 = std::integral_constant<int, 0>;
-    using I1 = std::integral_constant<int, 1>;
-    auto blocks = [&](auto self, auto q0c) -> void {
-      constexpr int q0 = decltype(q0c)::value;
-      constexpr int qn = q0 + 1 < R ? q0 + 1 : q0;
-      for (int kk = 0; kk + 2 < NWR; kk += 2) {
-        sweep_step(q0c, q0c, I0{}, kk, kk + 1, true);
-        sweep_step(q0c, q0c, I1{}, kk + 1, kk + 2, true);
-      }
-      sweep_step(q0c, q0c, I0{}, NWR - 2, NWR - 1, true);
-      sweep_step(q0c, std::integral_constant<int, qn>{}, I1{}, NWR - 1, 0, q0 + 1 < R);
-      if constexpr (q0 + 1 < R) self(self, std::integral_constant<int, q0 + 1>{});
-    };
-    blocks(blocks, I0{});
+    {
+      static_assert(NWR % 2 == 0, "pivots are processed in (even, odd) pairs");
+      using I0 = std::integral_constant<int, 0>;
+      using I1 = std::integral_constant<int, 1>;
+      auto blocks = [&](auto self, auto q0c) -> void {
+        constexpr int q0 = decltype(q0c)::value;
+        constexpr int qn = q0 + 1 < R ? q0 + 1 : q0;
+        for (int kk = 0; kk + 2 < NWR; kk += 2) {
+          sweep_step(q0c, q0c, I0{}, kk, kk + 1, true);
+          sweep_step(q0c, q0c, I1{}, kk + 1, kk + 2, true);
+        }
+        sweep_step(q0c, q0c, I0{}, NWR - 2, NWR - 1, true);
+        sweep_step(q0c, std::integral_constant<int, qn>{}, I1{}, NWR - 1, 0, q0 + 1 < R);
+        if constexpr (q0 + 1 < R) self(self, std::integral_constant<int, q0 + 1>{});
+      };
+      blocks(blocks, I0{});
+    }
   }
   if (is_row) {   // remove the +2 of the in-row diagonal copy, undo the Jacobi scaling
 #pragma unroll
@@ -539,7 +548,7 @@ solve_kernel(const SolveParams p) {
 #pragma unroll
       for (int c = 0; c < COLS; ++c) {
         const int col = rs * COLS + c;
-        const float v = col == rp + q * NWR ? diag[q] : row[q][c];
+        const float v = (!TC && col == rp + q * NWR) ? diag[q] : row[q][c];
         row[q][c] = v * sc[q] * (col < NW ? s_S[col] : 0.f);
       }
     if (CACHE && p.cache_pinv) {

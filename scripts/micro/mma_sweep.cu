@@ -54,7 +54,7 @@ __global__ void mma_rate(float* out, int reps) {
 // ---- 2. the blocked sweep ----------------------------------------------------------------------------
 constexpr int NP = 64;
 constexpr int YS = 12;   // row stride of Y in words: ldmatrix rows (16 B at 48 B stride) hit 8 distinct bank groups
-template <int MINB, bool SPLIT3>
+template <int MINB, bool SPLIT3, bool ROLL = false>
 __global__ __launch_bounds__(64, MINB) void sweep_mma(const float* __restrict__ Ain, float* __restrict__ out, int nmat, int nout,
                                                       long long* clk) {
   __shared__ __align__(16) float sL[NP][8];
@@ -77,15 +77,19 @@ __global__ __launch_bounds__(64, MINB) void sweep_mma(const float* __restrict__ 
   const int a_row = 32 * w + (lane & 7) + 8 * ((lane >> 3) & 1), a_col = 4 * (lane >> 4);
   const int b_row = 8 * (lane >> 4) + (lane & 7), b_col = 4 * ((lane >> 3) & 1);
   const long long t0 = clock64();
-#pragma unroll
+#pragma unroll(ROLL ? 1 : 8)
   for (int k = 0; k < 8; ++k) {
-    // a. publish column block k
+    // a. publish column block k (rolled loop: predicated stores instead of a dynamically indexed register array)
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      const int r0 = 32 * w + 16 * mt + g;
-      *reinterpret_cast<float2*>(&sL[r0][2 * t]) = make_float2(acc[mt][k][0], acc[mt][k][1]);
-      *reinterpret_cast<float2*>(&sL[r0 + 8][2 * t]) = make_float2(acc[mt][k][2], acc[mt][k][3]);
-    }
+    for (int nt = 0; nt < 8; ++nt)
+      if (nt == k) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const int r0 = 32 * w + 16 * mt + g;
+          *reinterpret_cast<float2*>(&sL[r0][2 * t]) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+          *reinterpret_cast<float2*>(&sL[r0 + 8][2 * t]) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+        }
+      }
     __syncthreads();
     // b. Cholesky of A_kk (every thread, redundantly: no exchange), own row of Y = L Lc^-T
     float lc[8][8], inv[8];
@@ -267,15 +271,29 @@ int main() {
            worst_id, cudaGetErrorString(cudaGetLastError()));
   }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int roll = 0; roll < 2; ++roll)
   for (int B : {1, 148, 592, 1184, 2368, 4736}) {
-    sweep_mma<8, true><<<B, 64>>>(dA, dO, nmat, 0, dclk);
+    auto kern = roll ? sweep_mma<8, true, true> : sweep_mma<8, true, false>;
+    kern<<<B, 64>>>(dA, dO, nmat, 0, dclk);
     cudaEventRecord(e0);
-    for (int r = 0; r < 10; ++r) sweep_mma<8, true><<<B, 64>>>(dA, dO, nmat, 0, dclk);
+    for (int r = 0; r < 10; ++r) kern<<<B, 64>>>(dA, dO, nmat, 0, dclk);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     long long c; cudaMemcpy(&c, dclk, 8, cudaMemcpyDeviceToHost);
-    printf("3xTF32 sweep: B = %4d (%4.1f CTAs/SM): %.2f us per launch, CTA 0 sweep = %lld cycles (%lld per 8-pivot block step)\n", B, B / 148.0,
-           ms * 100, c, c / 8);
+    printf("3xTF32 sweep (%s): B = %4d (%4.1f CTAs/SM): %.2f us per launch, CTA 0 sweep = %lld cycles (%lld per 8-pivot block step)\n",
+           roll ? "rolled" : "unrolled", B, B / 148.0, ms * 100, c, c / 8);
+  }
+  {  // the rolled kernel computes the same thing
+    sweep_mma<8, true, true><<<nmat, 64>>>(dA, dO, nmat, nmat, dclk);
+    std::vector<float> O2(A.size());
+    cudaMemcpy(O2.data(), dO, O2.size() * 4, cudaMemcpyDeviceToHost);
+    double d = 0;
+    for (size_t i = 0; i < O.size(); ++i) d = std::max(d, (double)std::fabs(O2[i]));
+    sweep_mma<8, true, false><<<nmat, 64>>>(dA, dO, nmat, nmat, dclk);
+    cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost);
+    double e = 0;
+    for (size_t i = 0; i < O.size(); ++i) e = std::max(e, (double)std::fabs(O2[i] - O[i]));
+    printf("rolled vs unrolled: max |diff| = %.3e (max |X| = %.3e)\n", e, d);
   }
   return 0;
 }

@@ -102,6 +102,7 @@ struct cmpc_handle {
   float* d_score = nullptr;      // LPT scheduling scratch
   int32_t* d_order = nullptr;
   int32_t* d_hist = nullptr;
+  int32_t* d_sched = nullptr;       // persistent-launch scheduling state, one block of kSchedInts per LPT slot range
   float4* d_cache_pinv = nullptr;   // cfg.cache_factorization
   float* d_cache_r = nullptr;
   uint8_t* d_cache_mask = nullptr;
@@ -141,14 +142,47 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-template <int N, int SPLIT, int MINB, int R = 1, bool CACHE = false, bool TC = false>
-cudaError_t launch_solve(const cmpc::SolveParams& p, cudaStream_t s) {
+// Batches of more than one wave of resident CTAs (SCHED instantiations, with the LPT order: p.sched is set by
+// schedule_batch) keep their hardest ranks on reserved, half-empty SMs (see "work distribution" in solve_kernel).
+// CMPC_NO_RESERVE=1 / CMPC_HARD_SM=<n> are experiment switches.
+template <int N, int SPLIT, int MINB, int R = 1, bool CACHE = false, bool TC = false, bool SCHED = false>
+cudaError_t launch_solve(const cmpc::SolveParams& p_in, cudaStream_t s) {
+  auto kernel = cmpc::solve_kernel<N, SPLIT, MINB, R, CACHE, TC, false>;
+  constexpr int THREADS = cmpc::Geo<N, SPLIT, R>::THREADS;
   if (TC) {   // 25 KB of static shared memory per CTA: MINB resident CTAs need the largest carve-out
-    static const cudaError_t carve = cudaFuncSetAttribute(cmpc::solve_kernel<N, SPLIT, MINB, R, CACHE, TC>,
-                                                          cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    static const cudaError_t carve = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (carve != cudaSuccess) return carve;
   }
-  return launch_pdl(cmpc::solve_kernel<N, SPLIT, MINB, R, CACHE, TC>, dim3((unsigned)p.B), dim3(cmpc::Geo<N, SPLIT, R>::THREADS), 0, s, p);
+  cmpc::SolveParams p = p_in;
+  if constexpr (SCHED) {
+    auto skernel = cmpc::solve_kernel<N, SPLIT, MINB, R, CACHE, TC, true>;
+    static const cudaError_t scarve = TC ? cudaFuncSetAttribute(skernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) : cudaSuccess;
+    if (scarve != cudaSuccess) return scarve;
+    static const int per_sm = [&] {      // resident CTAs of this kernel per SM
+      int per = 0;
+      return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, skernel, THREADS, 0) == cudaSuccess ? per : 0;
+    }();
+    static const int nsm = [&] {
+      int dev = 0, n = 0;
+      return cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess ? n : 0;
+    }();
+    const int wave = nsm * per_sm;       // CTAs the device holds at once
+    static const bool reserve_on = std::getenv("CMPC_NO_RESERVE") == nullptr;
+    static const int hard_sm = std::getenv("CMPC_HARD_SM") ? std::atoi(std::getenv("CMPC_HARD_SM")) : 32;
+    // every reserved SM must receive its kHardSlots hard workers in the first wave (B > wave), and the other
+    // SMs must be able to drain the main queue meanwhile
+    // ... and only batches of a few waves gain: in a long launch the hardest problems are over long before the end,
+    // and the rank assignment costs every CTA two L2 round trips (measured: 8192 problems -4 %, 4096 +6 %, 2048 +10 %)
+    if (p.sched && reserve_on && hard_sm > 0 && per_sm > cmpc::kHardSlots && nsm >= 2 * hard_sm && p.B > wave && p.B <= 5 * wave &&
+        hard_sm * cmpc::kHardSlots <= p.B / 4) {
+      p.n_hard_sm = hard_sm;
+      p.n_hard = hard_sm * cmpc::kHardSlots;
+      const int sleepers = hard_sm * (per_sm - cmpc::kHardSlots);   // as many spare CTAs as can sleep on the reserved SMs
+      return launch_pdl(skernel, dim3((unsigned)(p.B + sleepers)), dim3(THREADS), 0, s, p);
+    }
+  }
+  p.sched = nullptr;
+  return launch_pdl(kernel, dim3((unsigned)p.B), dim3(THREADS), 0, s, p);
 }
 // one thread-block cluster of CL CTAs per problem (long horizons, see cmpc_cluster.cuh)
 template <int NL, int CL, int SPLIT, int MINB>
@@ -216,9 +250,9 @@ const HorizonEntry kHorizons[] = {
     {4, {launch_solve<4, 1, 8>}, launch_condense<4>, launch_score<4>, nullptr},
     {5, {launch_solve<5, 1, 8>}, launch_condense<5>, launch_score<5>, nullptr},
     {8, {launch_solve<8, 1, 8>}, launch_condense<8>, launch_score<8>, nullptr},
-    {10, {launch_solve<10, 1, 8, 1, false, true>, launch_solve<10, 1, 8>, CMPC_X(launch_solve<10, 4, 2>),
+    {10, {launch_solve<10, 1, 8, 1, false, true, true>, launch_solve<10, 1, 8>, CMPC_X(launch_solve<10, 4, 2>),
           CMPC_X(launch_solve<10, 2, 8, 2>), CMPC_X(launch_solve<10, 5, 8, 5>), launch_solve_riccati<10, 8>},
-     launch_condense<10>, launch_score<10>, launch_solve<10, 1, 8, 1, true, true>},
+     launch_condense<10>, launch_score<10>, launch_solve<10, 1, 8, 1, true, true, true>},
     {12, {launch_solve<12, 2, 4>, nullptr, nullptr, nullptr, nullptr, launch_solve_riccati<12, 8>}, launch_condense<12>, launch_score<12>, nullptr},
     {16, {launch_solve<16, 2, 3>, nullptr, nullptr, nullptr, nullptr, launch_solve_riccati<16, 8>}, launch_condense<16>, launch_score<16>, nullptr},
     {20, {launch_solve_riccati<20, 6>, CMPC_X(launch_solve<20, 3, 1>), launch_solve_cluster<10, 2, 2, 3>, nullptr, nullptr,
@@ -302,6 +336,7 @@ void fill_solve_params(const cmpc_handle* h, cmpc::SolveParams& p) {
 // slots each cannot share that quotient).
 int schedule_batch(cmpc_handle* h, cmpc::SolveParams& p, cudaStream_t s) {
   p.order = nullptr;
+  p.sched = nullptr;
   if (!h->cfg.lpt_schedule || p.B < h->cfg.lpt_schedule) return CMPC_OK;
   if ((reinterpret_cast<uintptr_t>(p.r) & 15u) != 0) return CMPC_OK;   // score_kernel reads r with 16-byte loads
   const cmpc_config& c = h->cfg;
@@ -321,6 +356,7 @@ int schedule_batch(cmpc_handle* h, cmpc::SolveParams& p, cudaStream_t s) {
                       h->d_order + p.slot0, p.B));
   h->launches.fetch_add(2);
   p.order = h->d_order + p.slot0;
+  p.sched = h->d_sched + (size_t)cmpc::kSchedInts * hist_slot;   // used by the dense kernels for batches of more than one wave
   return CMPC_OK;
 }
 
@@ -579,6 +615,8 @@ int cmpc_create(const cmpc_config* cfg, cmpc_handle** out) {
       (e = cudaMalloc(&h->d_score, slots * sizeof(float))) != cudaSuccess ||
       (e = cudaMalloc(&h->d_order, slots * sizeof(int32_t))) != cudaSuccess ||
       (e = cudaMalloc(&h->d_hist, (size_t)h->hist_slots * 64 * sizeof(int32_t))) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_sched, (size_t)h->hist_slots * cmpc::kSchedInts * sizeof(int32_t))) != cudaSuccess ||
+      (e = cudaMemset(h->d_sched, 0, (size_t)h->hist_slots * cmpc::kSchedInts * sizeof(int32_t))) != cudaSuccess ||
       (e = cudaMemcpy(h->d_Minv, Mif.data(), mbytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemcpy(h->d_Mg, Mf.data(), mbytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemset(h->d_warm_x, 0, slots * 12 * N * sizeof(float))) != cudaSuccess ||
@@ -637,6 +675,7 @@ int cmpc_destroy(cmpc_handle* h) {
   cudaFree(h->d_score);
   cudaFree(h->d_order);
   cudaFree(h->d_hist);
+  cudaFree(h->d_sched);
   cudaFree(h->d_cache_pinv);
   cudaFree(h->d_cache_r);
   cudaFree(h->d_cache_mask);

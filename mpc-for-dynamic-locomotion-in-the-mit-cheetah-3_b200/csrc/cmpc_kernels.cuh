@@ -41,6 +41,13 @@ namespace cmpc {
 // lose accuracy).  Every finite tolerance >= 1e-5 exits long before, so iterates are unchanged.
 constexpr float kRhoAdaptFloor = 1e-6f;
 
+// scheduling state of a SCHED launch: [0] next main rank, [1] next hard rank, [2] CTAs that left,
+// [3] reserved-SM tickets, then per SM id (< kSchedSm): arrivals, role (0 unknown, 1 reserved, 2 normal),
+// hard problems in flight
+constexpr int kSchedSm = 256;
+constexpr int kSchedInts = 16 + 3 * kSchedSm;
+constexpr int kHardSlots = 4;         // CTAs of a reserved SM that serve the hard queue
+
 struct SolveParams {
   const float* __restrict__ x0;
   const float* __restrict__ r;
@@ -73,6 +80,11 @@ struct SolveParams {
   float rho_adapt_floor;              // kRhoAdaptFloor
   long long* dbg_clk;                 // debug: phase timestamps of CTA 0 (nullptr in production)
   long long* dbg_tl;                  // debug: [B][4] start ns, end ns, SM id, iterations of every CTA (nullptr in production)
+  // batches of more than one wave: CTAs take their launch-order rank when they start; the first n_hard ranks
+  // (the hardest by the LPT score) go to kHardSlots CTAs on each of n_hard_sm reserved SMs, whose other CTAs
+  // wait until those problems are done (see "work distribution" in solve_kernel)
+  int32_t* sched;                     // kSchedInts ints of scheduling state, all zero between launches
+  int32_t n_hard, n_hard_sm;
   // factorisation cache (closed-loop use, cfg.cache_factorization): -P^-1 of each slot's last
   // factorisation with the data it was computed for; nullptr = off
   float4* __restrict__ cache_pinv;    // [slots][NW*NWP/4 float4], laid out [tile piece][thread]
@@ -216,7 +228,8 @@ __device__ __forceinline__ float wrench_linear_term(int j, int a, const float* s
 // CACHE compiles the factorisation cache in (closed-loop instantiations); the default
 // instantiation carries none of its state through the register-limited ADMM loop.
 // TC runs the factorisation sweep on the tensor cores (cmpc_tc.cuh; one 64-thread CTA, 6N <= 64).
-template <int N, int SPLIT, int MINB, int R, bool CACHE, bool TC = false>
+// SCHED compiles the reserved-SM rank assignment in (p.sched; see "work distribution" below).
+template <int N, int SPLIT, int MINB, int R, bool CACHE, bool TC = false, bool SCHED = false>
 __global__ void __launch_bounds__((Geo<N, SPLIT, R>::THREADS), MINB)
 solve_kernel(const SolveParams p) {
   using G_ = Geo<N, SPLIT, R>;
@@ -243,20 +256,80 @@ solve_kernel(const SolveParams p) {
   __shared__ double s_e[2][NW];                         // stage errors of the linear term (fp64)
   __shared__ int s_mask[N];
 
-  if ((int)blockIdx.x >= p.B) return;
+  __shared__ int s_item;
+  __shared__ int s_sm[2];                 // SCHED, thread 0: SM id, hard item in flight
+  if (!SCHED && (int)blockIdx.x >= p.B) return;
   grid_dependency_wait();
-  const int b = p.order ? p.order[blockIdx.x] : (int)blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const bool leg_warp = warp < LWARPS;   // warp-uniform: warps without leg threads skip leg phases
+
+  // ---- work distribution --------------------------------------------------------------------------
+  // !SCHED: CTA i solves rank i of the launch order.  SCHED: still one problem per CTA, but a CTA takes
+  // its rank when it starts, by the role of the SM it landed on.  A CTA's iteration latency doubles
+  // between an idle and a full SM (gpu_iter_latency.py) and the batch ends when its hardest problem does,
+  // so the n_hard hardest ranks are kept off the full SMs: the first n_hard_sm SMs to report are reserved,
+  // the first kHardSlots CTAs of a reserved SM take ranks from the hard queue, and every other CTA that
+  // lands there sleeps until that queue is empty and this SM's hard problems are solved (it holds a CTA
+  // slot but no issue slots; the hardware keeps placing the remaining CTAs on the other SMs).  Everybody
+  // else takes the next main rank, or a hard one when the main queue is empty.  The grid has as many CTAs
+  // more than ranks as there can be sleepers, so a sleeper that wakes up to empty queues leaves without
+  // work instead of starting one of the last problems late.  Thread 0 only; nothing stays in registers.
+  int item = (int)blockIdx.x;
+  if constexpr (SCHED) {
+    if (tid == 0) {
+      int* S = p.sched;
+      const int nh = p.n_hard, nm = p.B - nh;
+      int sm_id, role = 2, arrival = kHardSlots;
+      asm volatile("mov.u32 %0, %smid;" : "=r"(sm_id));
+      if (sm_id >= kSchedSm) sm_id = kSchedSm - 1;
+      int* running = S + 16 + 2 * kSchedSm + sm_id;
+      {
+        // the role of an SM is fixed by its first CTA; CTAs of later waves on the ordinary SMs (the common case)
+        // pay one load for it, and only reserved SMs count their arrivals further
+        volatile int* rp_ = S + 16 + kSchedSm + sm_id;
+        role = *rp_;
+        if (role != 2) {
+          arrival = atomicAdd(S + 16 + sm_id, 1);
+          if (arrival == 0) {
+            role = atomicAdd(S + 3, 1) < p.n_hard_sm ? 1 : 2;
+            atomicExch(S + 16 + kSchedSm + sm_id, role);
+          } else {
+            while ((role = *rp_) == 0) __nanosleep(100);   // the first CTA of this SM is about to set it
+          }
+        }
+      }
+      int got = p.B, hard = 0;
+      const bool reserved = role == 1, hard_worker = reserved && arrival < kHardSlots;
+      if (reserved && !hard_worker)
+        while (atomicAdd(S + 1, 0) < nh || atomicAdd(running, 0) > 0) __nanosleep(500);
+      if (hard_worker && atomicAdd(S + 1, 0) < nh) {
+        atomicAdd(running, 1);          // before the take: the sleepers never see "empty and idle" early
+        const int h = atomicAdd(S + 1, 1);
+        if (h < nh) { got = h; hard = 1; }
+        else atomicSub(running, 1);
+      }
+      if (got == p.B) {
+        const int m = atomicAdd(S, 1);
+        if (m < nm) got = nh + m;
+      }
+      if (got == p.B && nh > 0 && atomicAdd(S + 1, 0) < nh) { const int h = atomicAdd(S + 1, 1); if (h < nh) got = h; }   // main queue empty: a hard rank may be left
+      s_item = got;
+      s_sm[0] = sm_id; s_sm[1] = hard;
+    }
+    __syncthreads();
+    item = s_item;
+  }
+  if (!SCHED || item < p.B) {   // SCHED launches a few CTAs more than ranks: a CTA that wakes up to empty queues just leaves
+  const int b = p.order ? p.order[item] : item;
   const int slot = p.slot0 + b;
 
   if (p.dbg_tl && tid == 0) {
     unsigned long long t; unsigned sm;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
-    p.dbg_tl[4 * (size_t)blockIdx.x] = (long long)t;
-    p.dbg_tl[4 * (size_t)blockIdx.x + 2] = sm;
+    p.dbg_tl[4 * (size_t)item] = (long long)t;
+    p.dbg_tl[4 * (size_t)item + 2] = sm;
   }
   if (p.dbg_clk && blockIdx.x == 0 && tid == 0) p.dbg_clk[0] = clock64();
   // ---- phase 0: stage the per-problem record (coalesced 4-byte loads, every byte requested
@@ -863,7 +936,7 @@ solve_kernel(const SolveParams p) {
   }
   if (tid == 0) {
     if (p.iters) p.iters[b] = it;
-    if (p.dbg_tl) p.dbg_tl[4 * (size_t)blockIdx.x + 3] = it;
+    if (p.dbg_tl) p.dbg_tl[4 * (size_t)(SCHED ? s_item : (int)blockIdx.x) + 3] = it;
     if (p.pri_res) p.pri_res[b] = pri;
     if (p.dua_res) p.dua_res[b] = dua;
     if (p.status) p.status[b] = status;
@@ -933,7 +1006,19 @@ solve_kernel(const SolveParams p) {
   if (p.dbg_tl && tid == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    p.dbg_tl[4 * (size_t)blockIdx.x + 1] = (long long)t;
+    p.dbg_tl[4 * (size_t)(SCHED ? s_item : (int)blockIdx.x) + 1] = (long long)t;
+  }
+  }
+  if constexpr (SCHED) {
+    if (tid == 0) {
+      if (s_sm[1]) atomicSub(p.sched + 16 + 2 * kSchedSm + s_sm[0], 1);   // wakes this SM's sleepers when it was the last
+      __threadfence();
+      s_sm[1] = atomicAdd(p.sched + 2, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_sm[1]) {   // the last CTA to leave zeroes the scheduling state for the next launch
+      for (int i = tid; i < kSchedInts; i += THREADS) p.sched[i] = 0;
+    }
   }
 }
 

@@ -43,9 +43,9 @@ constexpr float kRhoAdaptFloor = 1e-6f;
 
 // scheduling state of a SCHED launch: [0] next main rank, [1] next hard rank, [2] CTAs that left,
 // [3] reserved-SM tickets, then per SM id (< kSchedSm): arrivals, role (0 unknown, 1 reserved, 2 normal),
-// hard problems in flight
+// hard problems in flight, hard workers that have made their take
 constexpr int kSchedSm = 256;
-constexpr int kSchedInts = 16 + 3 * kSchedSm;
+constexpr int kSchedInts = 16 + 4 * kSchedSm;
 constexpr int kHardSlots = 4;         // CTAs of a reserved SM that serve the hard queue
 
 struct SolveParams {
@@ -270,8 +270,8 @@ solve_kernel(const SolveParams p) {
   // between an idle and a full SM (gpu_iter_latency.py) and the batch ends when its hardest problem does,
   // so the n_hard hardest ranks are kept off the full SMs: the first n_hard_sm SMs to report are reserved,
   // the first kHardSlots CTAs of a reserved SM take ranks from the hard queue, and every other CTA that
-  // lands there sleeps until that queue is empty and this SM's hard problems are solved (it holds a CTA
-  // slot but no issue slots; the hardware keeps placing the remaining CTAs on the other SMs).  Everybody
+  // lands there sleeps until this SM's hard problems are solved (it holds a CTA slot but no issue slots;
+  // the hardware keeps placing the remaining CTAs on the other SMs).  Everybody
   // else takes the next main rank, or a hard one when the main queue is empty.  The grid has as many CTAs
   // more than ranks as there can be sleepers, so a sleeper that wakes up to empty queues leaves without
   // work instead of starting one of the last problems late.  Thread 0 only; nothing stays in registers.
@@ -301,13 +301,21 @@ solve_kernel(const SolveParams p) {
       }
       int got = p.B, hard = 0;
       const bool reserved = role == 1, hard_worker = reserved && arrival < kHardSlots;
+      // A sleeper waits for this SM only: for its kHardSlots hard workers (they arrived before it and do not
+      // block) to have made their take, and for the hard problems they took to be solved.  It never waits for
+      // the queues, so no CTA placement by the hardware (other kernels on the device) can stall the launch.
+      int* settled = S + 16 + 3 * kSchedSm + sm_id;
       if (reserved && !hard_worker)
-        while (atomicAdd(S + 1, 0) < nh || atomicAdd(running, 0) > 0) __nanosleep(500);
-      if (hard_worker && atomicAdd(S + 1, 0) < nh) {
-        atomicAdd(running, 1);          // before the take: the sleepers never see "empty and idle" early
-        const int h = atomicAdd(S + 1, 1);
-        if (h < nh) { got = h; hard = 1; }
-        else atomicSub(running, 1);
+        while (atomicAdd(settled, 0) < kHardSlots || atomicAdd(running, 0) > 0) __nanosleep(500);
+      if (hard_worker) {
+        if (atomicAdd(S + 1, 0) < nh) {
+          atomicAdd(running, 1);
+          const int h = atomicAdd(S + 1, 1);
+          if (h < nh) { got = h; hard = 1; }
+          else atomicSub(running, 1);
+        }
+        __threadfence();                // `running` is up before this worker counts as settled
+        atomicAdd(settled, 1);
       }
       if (got == p.B) {
         const int m = atomicAdd(S, 1);

@@ -213,6 +213,38 @@ def test_warm_start_semantics():
     assert np.array_equal(U4.cpu().numpy(), U2.cpu().numpy())
 
 
+@pytest.mark.timeout(300)
+def test_reserved_sm_rank_assignment_is_transparent():
+    """Batches of 1-5 waves of CTAs take their launch rank when a CTA starts, the hardest ranks on
+    reserved SMs (solve_kernel "work distribution"): results must be those of the plain one-CTA-per-rank
+    launch - compared with the same problems solved in sub-batches of less than one wave - whatever the
+    batch size, also when two such launches share the device (staged host path: two chunks, two streams)
+    and when launches follow each other on one handle (the scheduling state is re-zeroed by the kernel)."""
+    def in_sub_batches(q):
+        parts = [gpu_solve(q.slice(a, min(a + 1000, q.B)), warm_mode=0) for a in range(0, q.B, 1000)]
+        return np.concatenate([x["U"] for x in parts]), np.concatenate([x["iters"] for x in parts])
+    big = synthetic_batch(5921, N=10, seed=0)
+    big_U, big_it = in_sub_batches(big)
+    pb = big.slice(0, 4096)
+    ref_U, ref_it = big_U[:4096], big_it[:4096]
+    mpc = pkg.BatchedMPC(N=10, max_batch=pb.B, warm_mode=0)
+    args = dev_args(pb)
+    for _ in range(3):                                   # repeated launches on the same scheduling state
+        U, X, st = mpc.solve(*args)
+        torch.cuda.synchronize()
+        assert np.array_equal(U.cpu().numpy().astype(np.float64), ref_U)
+        assert np.array_equal(st.iters.cpu().numpy(), ref_it)
+    for B in (1185, 1500, 2048, 3000, 5920, 5921):       # around the one-wave and five-wave limits
+        d = gpu_solve(big.slice(0, B), warm_mode=0)
+        assert np.array_equal(d["U"], big_U[:B]) and np.array_equal(d["iters"], big_it[:B]), B
+        assert np.all(d["status"] == 1)
+    hin = [torch.from_numpy(a).pin_memory().numpy() for a in pb.f32()]
+    m2 = pkg.BatchedMPC(N=10, max_batch=pb.B, warm_mode=0, host_zero_copy=0)
+    for _ in range(2):
+        Uh, Xh, sh = m2.solve_host(*hin)
+        assert np.array_equal(Uh.astype(np.float64), ref_U) and np.array_equal(sh.iters, ref_it)
+
+
 def test_host_path_matches_device_path_and_sharding():
     """cmpc_solve_host (pinned staging, chunked streams) returns bit-identical results to
     cmpc_solve, and solving two half batches equals solving the whole batch (problems are

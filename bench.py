@@ -480,7 +480,7 @@ def run_ours(args):
     fr_fp32 = flops * B / kern_s / fp32_peak
     fr_smem = smem_b * B / kern_s / smem_peak
     fr_hbm = ach_gbs / hbm_peak
-    kname = f"cmpc::solve_kernel<{N},...> (dense)" if N <= 16 else f"cmpc::solve_riccati_kernel<{N},...> (stage-wise)"
+    kname = f"cmpc::solve_kernel<{N},...> (dense" + (", tensor-core sweep)" if N == 10 else ")") if N <= 16 else f"cmpc::solve_riccati_kernel<{N},...> (stage-wise)"
     # the roofline fraction is the LARGEST of the three (FP32 pipe, shared memory, HBM)
     binding = max((fr_fp32, "fp32"), (fr_hbm, "hbm"))
     roof = {"bound": binding[1],

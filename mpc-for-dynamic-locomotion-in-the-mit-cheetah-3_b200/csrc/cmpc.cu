@@ -149,14 +149,17 @@ template <int N, int SPLIT, int MINB, int R = 1, bool CACHE = false, bool TC = f
 cudaError_t launch_solve(const cmpc::SolveParams& p_in, cudaStream_t s) {
   auto kernel = cmpc::solve_kernel<N, SPLIT, MINB, R, CACHE, TC, false>;
   constexpr int THREADS = cmpc::Geo<N, SPLIT, R>::THREADS;
-  if (TC) {   // 25 KB of static shared memory per CTA: MINB resident CTAs need the largest carve-out
-    static const cudaError_t carve = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  // 24 KB of static shared memory per CTA: MINB resident CTAs need the 196 KB carve-out (86 % of 228 KB); the
+  // remaining 60 KB of L1 hold the register spills of the ADMM loop (CMPC_CARVEOUT=<percent> overrides)
+  static const int carve_pct = std::getenv("CMPC_CARVEOUT") ? std::atoi(std::getenv("CMPC_CARVEOUT")) : 70;
+  if (TC) {
+    static const cudaError_t carve = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve_pct);
     if (carve != cudaSuccess) return carve;
   }
   cmpc::SolveParams p = p_in;
   if constexpr (SCHED) {
     auto skernel = cmpc::solve_kernel<N, SPLIT, MINB, R, CACHE, TC, true>;
-    static const cudaError_t scarve = TC ? cudaFuncSetAttribute(skernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) : cudaSuccess;
+    static const cudaError_t scarve = TC ? cudaFuncSetAttribute(skernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve_pct) : cudaSuccess;
     if (scarve != cudaSuccess) return scarve;
     static const int per_sm = [&] {      // resident CTAs of this kernel per SM
       int per = 0;
@@ -250,9 +253,9 @@ const HorizonEntry kHorizons[] = {
     {4, {launch_solve<4, 1, 8>}, launch_condense<4>, launch_score<4>, nullptr},
     {5, {launch_solve<5, 1, 8>}, launch_condense<5>, launch_score<5>, nullptr},
     {8, {launch_solve<8, 1, 8>}, launch_condense<8>, launch_score<8>, nullptr},
-    {10, {launch_solve<10, 1, 8, 1, false, true, true>, launch_solve<10, 1, 8>, CMPC_X(launch_solve<10, 4, 2>),
+    {10, {launch_solve<10, 1, 6, 1, false, true, true>, launch_solve<10, 1, 8>, launch_solve<10, 1, 8, 1, false, true, true>,
           CMPC_X(launch_solve<10, 2, 8, 2>), CMPC_X(launch_solve<10, 5, 8, 5>), launch_solve_riccati<10, 8>},
-     launch_condense<10>, launch_score<10>, launch_solve<10, 1, 8, 1, true, true, true>},
+     launch_condense<10>, launch_score<10>, launch_solve<10, 1, 6, 1, true, true, true>},
     {12, {launch_solve<12, 2, 4>, nullptr, nullptr, nullptr, nullptr, launch_solve_riccati<12, 8>}, launch_condense<12>, launch_score<12>, nullptr},
     {16, {launch_solve<16, 2, 3>, nullptr, nullptr, nullptr, nullptr, launch_solve_riccati<16, 8>}, launch_condense<16>, launch_score<16>, nullptr},
     {20, {launch_solve_riccati<20, 6>, CMPC_X(launch_solve<20, 3, 1>), launch_solve_cluster<10, 2, 2, 3>, nullptr, nullptr,

@@ -236,7 +236,7 @@ solve_kernel(const SolveParams p) {
   constexpr int NW = G_::NW, NWP = G_::NWP, COLS = G_::COLS, NLEG = G_::NLEG, NWR = G_::NWR;
   constexpr int THREADS = G_::THREADS, LWARPS = G_::LWARPS, NX = G_::NX;
   static_assert(!TC || (SPLIT == 1 && R == 1 && THREADS == kTcN && NW <= kTcN), "tensor-core sweep: one row per thread, 64 threads");
-  __shared__ __align__(16) float s_P[TC ? kTcSmemFloats : 4];   // row <-> fragment staging of the tensor-core sweep
+  __shared__ __align__(16) float s_P[TC ? tc_smem_floats<NW>() : 4];   // row <-> fragment staging of the tensor-core sweep
 
   __shared__ __align__(16) float s_x0[16];
   __shared__ __align__(16) float s_xd[NX + 3];         // x_des; reused to stage U at the end
@@ -305,8 +305,13 @@ solve_kernel(const SolveParams p) {
       // block) to have made their take, and for the hard problems they took to be solved.  It never waits for
       // the queues, so no CTA placement by the hardware (other kernels on the device) can stall the launch.
       int* settled = S + 16 + 3 * kSchedSm + sm_id;
-      if (reserved && !hard_worker)
-        while (atomicAdd(settled, 0) < kHardSlots || atomicAdd(running, 0) > 0) __nanosleep(500);
+      if (reserved && !hard_worker) {
+        unsigned ns = 250;              // back off to ~4 us between polls: a hard problem runs for 50-250 us
+        while (*(volatile int*)settled < kHardSlots || *(volatile int*)running > 0) {
+          __nanosleep(ns);
+          if (ns < 4000) ns *= 2;
+        }
+      }
       if (hard_worker) {
         if (atomicAdd(S + 1, 0) < nh) {
           atomicAdd(running, 1);

@@ -32,7 +32,11 @@ namespace cmpc {
 constexpr int kTcN = 64;                        // padded matrix size (rows 6N .. 63: identity)
 constexpr int kTcPS = 68;                       // row stride (words) of the row <-> fragment staging area
 constexpr int kTcYS = 12;                       // row stride of the panel Y: ldmatrix rows on 8 distinct bank groups
-constexpr int kTcSmemFloats = kTcN * kTcPS;     // 17 KB; the panels alias its front during the block steps
+// staging rows of one matrix: the identity padding rows are generated in registers, not staged, so that 8 CTAs
+// (this area + 7.4 KB of solver state + 1 KB reserved each) fit the 196 KB shared-memory carve-out and leave
+// 60 KB of L1 to the register spills of the ADMM loop (measured: with the 228 KB carve-out they go to L2)
+template <int NW>
+__host__ __device__ constexpr int tc_smem_floats() { return NW * kTcPS > kTcN * (8 + 2 * kTcYS) ? NW * kTcPS : kTcN * (8 + 2 * kTcYS); }
 
 __device__ __forceinline__ float tf32_round(float x) {
   uint32_t r;
@@ -54,26 +58,19 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const float* p) {
 // Called by all 64 threads of the CTA (two full warps: mma.sync / ldmatrix are warp-collective).
 //   in : row[0 .. NW) = row `tid` of A (unit diagonal) for tid < NW; threads NW .. 63 own the identity padding
 //   out: row[0 .. NW) = row `tid` of -A^-1
-// sP: kTcSmemFloats floats of shared memory, 16-byte aligned, owned by this call between its barriers.
+// sP: tc_smem_floats<NW>() floats of shared memory, 16-byte aligned, owned by this call between its barriers.
 template <int NW, int NWP>
 __device__ __forceinline__ void tc_sweep(float (&row)[NWP], float* __restrict__ sP, const int tid) {
   static_assert(NW <= kTcN && NW % 4 == 0 && NWP >= NW, "one 64 x 64 fragment matrix per CTA");
   const int lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
   // ---- rows -> staging area, negated: the accumulators hold -A, so the update is acc += Y Y' ----
-  {
+  if (tid < NW) {
     float* mine = sP + tid * kTcPS;
-    if (tid < NW) {
 #pragma unroll
-      for (int c = 0; c < NW; c += 4)
-        *reinterpret_cast<float4*>(mine + c) = make_float4(-row[c], -row[c + 1], -row[c + 2], -row[c + 3]);
+    for (int c = 0; c < NW; c += 4)
+      *reinterpret_cast<float4*>(mine + c) = make_float4(-row[c], -row[c + 1], -row[c + 2], -row[c + 3]);
 #pragma unroll
-      for (int c = NW; c < kTcN; c += 4) *reinterpret_cast<float4*>(mine + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-    } else {
-#pragma unroll
-      for (int c = 0; c < kTcN; c += 4)
-        *reinterpret_cast<float4*>(mine + c) = make_float4(c == tid ? -1.f : 0.f, c + 1 == tid ? -1.f : 0.f,
-                                                           c + 2 == tid ? -1.f : 0.f, c + 3 == tid ? -1.f : 0.f);
-    }
+    for (int c = NW; c < kTcN; c += 4) *reinterpret_cast<float4*>(mine + c) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
   float acc[2][8][4];       // rows 32w + 16mt + {g, g+8}, columns 8nt + {2t, 2t+1}
@@ -81,9 +78,12 @@ __device__ __forceinline__ void tc_sweep(float (&row)[NWP], float* __restrict__ 
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float* q = sP + (32 * w + 16 * mt + g) * kTcPS + 8 * nt + 2 * t;
-      const float2 u = *reinterpret_cast<const float2*>(q);
-      const float2 v = *reinterpret_cast<const float2*>(q + 8 * kTcPS);
+      const int r0 = 32 * w + 16 * mt + g, r1 = r0 + 8, c0 = 8 * nt + 2 * t;
+      // rows >= NW are the identity padding (-I in the negated matrix)
+      const float2 u = r0 < NW ? *reinterpret_cast<const float2*>(sP + r0 * kTcPS + c0)
+                               : make_float2(r0 == c0 ? -1.f : 0.f, r0 == c0 + 1 ? -1.f : 0.f);
+      const float2 v = r1 < NW ? *reinterpret_cast<const float2*>(sP + r1 * kTcPS + c0)
+                               : make_float2(r1 == c0 ? -1.f : 0.f, r1 == c0 + 1 ? -1.f : 0.f);
       acc[mt][nt][0] = u.x; acc[mt][nt][1] = u.y; acc[mt][nt][2] = v.x; acc[mt][nt][3] = v.y;
     }
   __syncthreads();          // the staging area becomes the panels
@@ -184,13 +184,15 @@ __device__ __forceinline__ void tc_sweep(float (&row)[NWP], float* __restrict__ 
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      float* q = sP + (32 * w + 16 * mt + g) * kTcPS + 8 * nt + 2 * t;
-      *reinterpret_cast<float2*>(q) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
-      *reinterpret_cast<float2*>(q + 8 * kTcPS) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+      const int r0 = 32 * w + 16 * mt + g, r1 = r0 + 8;
+      float* q = sP + r0 * kTcPS + 8 * nt + 2 * t;
+      if (r0 < NW) *reinterpret_cast<float2*>(q) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+      if (r1 < NW) *reinterpret_cast<float2*>(q + 8 * kTcPS) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
     }
   __syncthreads();
-  {   // every thread, padding rows included: `row` must be dead across the sweep (it shares the register file with acc)
-    const float* mine = sP + tid * kTcPS;
+  {   // every thread (the padding threads re-read the last row): `row` must be dead across the sweep, it shares
+      // the register file with acc
+    const float* mine = sP + (tid < NW ? tid : NW - 1) * kTcPS;
 #pragma unroll
     for (int c = 0; c < NW; c += 4) {
       const float4 v = *reinterpret_cast<const float4*>(mine + c);

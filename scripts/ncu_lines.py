@@ -1,7 +1,8 @@
 """Aggregate an `ncu --page source --csv --print-source cuda,sass` export by source line.
 usage: ncu -i X.ncu-rep --page source --csv --print-source cuda,sass > x.csv; python scripts/ncu_lines.py x.csv [top]"""
 import csv, sys, collections
-rows = list(csv.reader(open(sys.argv[1])))
+# ncu does not escape quotes inside the source column (inline asm): split on the field separator instead of csv.reader
+rows = [l.rstrip('\n')[1:-1].split('","') if l.startswith('"') else next(csv.reader([l])) for l in open(sys.argv[1]) if l.strip()]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 hdr = None
 agg = collections.OrderedDict()

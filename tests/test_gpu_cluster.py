@@ -17,8 +17,8 @@ from test_gpu_parity import gpu_solve, close, ATOL, RTOL, _FakeLite3, _Logger   
                                              (60, 0, ("pseudo_gallop",)), (30, 0, GAIT_NAMES), (20, 0, GAIT_NAMES),
                                              # register-blocked single-CTA layouts <N,SPLIT,MINB,R>
                                              (10, 3, GAIT_NAMES), (10, 4, GAIT_NAMES), (30, 0, ("trot",)),
-                                             # dense kernel with the factorisation sweep on the tensor cores
-                                             (10, 1, GAIT_NAMES), (10, 1, ("trot",)),
+                                             # N = 10: variant 1 = SIMT sweep, variant 2 = tensor-core sweep at 8 CTAs/SM (default: tensor-core sweep, 6 CTAs/SM)
+                                             (10, 1, GAIT_NAMES), (10, 1, ("trot",)), (10, 2, GAIT_NAMES),
                                              (30, 1, GAIT_NAMES), (30, 3, ("trot",)), (30, 4, GAIT_NAMES),
                                              # variant 5 = the other formulation: stage-wise (Riccati) kernel
                                              # for N <= 16 (default: dense), dense / cluster kernel for N >= 20

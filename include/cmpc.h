@@ -85,8 +85,11 @@ typedef struct cmpc_config {
   int32_t adaptive_rho_interval; /* OSQP-style rho adaptation every k iterations, 0 = off */
   float adaptive_rho_tolerance;  /* refactor when rho changes by more than this factor (5) */
   float rho_min, rho_max;        /* clamp of the adapted rho                                 */
-  int32_t kernel_variant; /* 0 = default thread layout; >0 selects an alternative where one is
-                             compiled (cmpc_has_variant), else the default; see DESIGN.md */
+  int32_t kernel_variant; /* 0 = default kernel of the horizon; >0 selects an alternative where one is
+                             compiled (cmpc_has_variant), else the default.  N = 10: 1 = SIMT factorisation
+                             sweep (default: tensor cores), 2 = tensor-core sweep at 8 CTAs/SM, 5 = stage-wise
+                             (Riccati) kernel; N >= 20: 5 = dense / cluster kernel (default: Riccati), 2 =
+                             cluster kernel (N = 20, 30); see DESIGN.md 4 */
   int32_t lpt_schedule; /* >0: batches of at least this size are launched hardest-first
                            (conditioning score), 0 = launch in batch order               */
   int32_t device;       /* CUDA device ordinal                                       */

@@ -235,7 +235,10 @@ struct HorizonEntry {
 // Horizons with compiled kernels.  Dense kernels <N, SPLIT, MINB, R>: a thread owns an R x (6N/SPLIT)
 // register tile of the 6N x 6N wrench matrix (R rows, one of SPLIT column slices), <= 96 floats.
 // Slot 0 is the default kernel of the horizon:
-//   N <= 16: dense single-CTA kernel (cmpc_kernels.cuh);
+//   N <= 16: dense single-CTA kernel (cmpc_kernels.cuh); N = 10: <10, 1, MINB = 6, 1, CACHE, TC, SCHED> = factorisation
+//            sweep on the tensor cores (cmpc_tc.cuh), 6 CTAs/SM at 168 registers, reserved-SM rank assignment for
+//            batches of 1-5 waves; slot 1 = the SIMT sweep at 8 CTAs/SM (round-1 layout), slot 2 = tensor-core sweep
+//            at 8 CTAs/SM / 128 registers (scripts/gpu_tc_exp.py, gpu_carve_exp.py, gpu_reserve_exp.py);
 //   N >= 20: stage-wise Riccati kernel (cmpc_riccati.cuh), measured on B200 against the dense / cluster
 //            kernels: N=20 1.5x at 16384 problems (equal at 4096), N=30 2.25x (config 4), N=40 3.4x, N=60 5.2x
 //            (scripts/gpu_riccati_exp.py, gpu_n20_kernels.py).

@@ -234,7 +234,7 @@ def test_reserved_sm_rank_assignment_is_transparent():
         torch.cuda.synchronize()
         assert np.array_equal(U.cpu().numpy().astype(np.float64), ref_U)
         assert np.array_equal(st.iters.cpu().numpy(), ref_it)
-    for B in (1185, 1500, 2048, 3000, 5920, 5921):       # around the one-wave and five-wave limits
+    for B in (888, 889, 1185, 2048, 4440, 4441, 5920, 5921):   # around the one- and five-wave limits at 6 / 8 CTAs per SM
         d = gpu_solve(big.slice(0, B), warm_mode=0)
         assert np.array_equal(d["U"], big_U[:B]) and np.array_equal(d["iters"], big_it[:B]), B
         assert np.all(d["status"] == 1)

@@ -412,6 +412,7 @@ int solve_device(cmpc_handle* h, int B, int slot0, const float* x0, const float*
   h->launches.fetch_add(1);
   if (tl_path) {   // per-CTA timeline of this launch: [B][4] int64 (start ns, end ns, SM, iterations), launch order
     std::vector<long long> tl((size_t)B * 4);
+    CUDA_TRY(cudaStreamSynchronize(s));   // the launching stream may be a non-blocking one
     CUDA_TRY(cudaMemcpy(tl.data(), p.dbg_tl, tl.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(p.dbg_tl);
     if (FILE* f = std::fopen(tl_path, "wb")) { std::fwrite(tl.data(), sizeof(long long), tl.size(), f); std::fclose(f); }

@@ -349,7 +349,9 @@ int schedule_batch(cmpc_handle* h, cmpc::SolveParams& p, cudaStream_t s) {
   const int hist_slot = p.slot0 / c.lpt_schedule;
   if (hist_slot >= h->hist_slots) return CMPC_OK;
   cmpc::ScoreParams sp{};
-  sp.x0 = p.x0; sp.r = p.r; sp.mask = p.mask; sp.Mg = h->d_Mg;
+  sp.x0 = p.x0; sp.r = p.r; sp.mask = p.mask; sp.Mg = h->d_Mg; sp.mu = p.mu;
+  static const int score_mode = std::getenv("CMPC_SCORE") ? std::atoi(std::getenv("CMPC_SCORE")) : 0;   // experiment switch
+  sp.mode = score_mode;
   sp.score = h->d_score + p.slot0;
   sp.hist = h->d_hist + 64 * hist_slot;
   sp.B = p.B;

@@ -1047,6 +1047,9 @@ struct ScoreParams {
   const float* __restrict__ r;
   const uint8_t* __restrict__ mask;
   const float* __restrict__ Mg;
+  const float* __restrict__ mu;
+  int32_t mode;                 // 0 = mean diagonal of H x horizontal lever arms / mu (default), 1 = mean diagonal of H
+                                // (round 1), 2 = lever arms / mu
   float* __restrict__ score;
   int32_t* __restrict__ hist;   // [64], zeroed by the host before the launch
   int32_t B;
@@ -1060,8 +1063,36 @@ __device__ __forceinline__ int score_bucket(float s) {
   return q < 0 ? 0 : (q > 63 ? 63 : q);
 }
 
+// Mean over the stance legs of the first and last stage of the squared horizontal lever arm, over mu.  Measured
+// on the iteration counts of configs 2 / 3 (profiles/r02_lpt_score_study.txt), for the product with the mean
+// diagonal of H (the default score): 93 / 72 of the 96 hardest of 3000 problems in the first 384 ranks against
+// 83 / 59 for the mean diagonal of H alone, and no 235-iteration problem among the last ranks of a mixed-gait
+// batch (the lever arms alone find the hard problems as well but rank the easy ones worse).
+template <int N>
+__device__ __forceinline__ float problem_score_arms(const ScoreParams& p, int b) {
+  float acc = 0.f;
+  int cnt = 0;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int j = e == 0 ? 0 : N - 1;
+    const int m = __ldg(p.mask + (size_t)b * N + j);
+    const float4* rq = reinterpret_cast<const float4*>(p.r + ((size_t)b * N + j) * 12);
+    const float4 q0 = __ldg(rq), q1 = __ldg(rq + 1), q2 = __ldg(rq + 2);
+    const float rr[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+      if ((m >> l) & 1) {
+        acc += rr[3 * l] * rr[3 * l] + rr[3 * l + 1] * rr[3 * l + 1];
+        ++cnt;
+      }
+  }
+  return cnt ? acc / ((float)cnt * fmaxf(__ldg(p.mu + b), 1e-3f)) : 0.f;
+}
+
 template <int N>
 __device__ __forceinline__ float problem_score(const ScoreParams& p, int b) {
+  if (p.mode == 2) return 64.f * problem_score_arms<N>(p, b);          // x64: centred in the bucket range
+  const float arms = p.mode == 0 ? problem_score_arms<N>(p, b) : 1.f;
   float sn, cs;
   sincosf(__ldg(p.x0 + (size_t)b * 13 + 2), &sn, &cs);
   float acc = 0.f;
@@ -1090,7 +1121,7 @@ __device__ __forceinline__ float problem_score(const ScoreParams& p, int b) {
       cnt += 3;
     }
   }
-  return cnt ? acc / (float)cnt : 0.f;
+  return cnt ? arms * acc / (float)cnt : 0.f;
 }
 
 template <int N>

@@ -142,7 +142,7 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-// Batches of more than one wave of resident CTAs (SCHED instantiations, with the LPT order: p.sched is set by
+// Batches of 1.5-4 waves of resident CTAs (SCHED instantiations, with the LPT order: p.sched is set by
 // schedule_batch) keep their hardest ranks on reserved, half-empty SMs (see "work distribution" in solve_kernel).
 // CMPC_NO_RESERVE=1 / CMPC_HARD_SM=<n> are experiment switches.
 template <int N, int SPLIT, int MINB, int R = 1, bool CACHE = false, bool TC = false, bool SCHED = false>
@@ -174,9 +174,10 @@ cudaError_t launch_solve(const cmpc::SolveParams& p_in, cudaStream_t s) {
     static const int hard_sm = std::getenv("CMPC_HARD_SM") ? std::atoi(std::getenv("CMPC_HARD_SM")) : 32;
     // every reserved SM must receive its kHardSlots hard workers in the first wave (B > wave), and the other
     // SMs must be able to drain the main queue meanwhile
-    // ... and only batches of a few waves gain: in a long launch the hardest problems are over long before the end,
-    // and the rank assignment costs every CTA two L2 round trips (measured: 8192 problems -4 %, 4096 +6 %, 2048 +10 %)
-    if (p.sched && reserve_on && hard_sm > 0 && per_sm > cmpc::kHardSlots && nsm >= 2 * hard_sm && p.B > wave && p.B <= 5 * wave &&
+    // ... and only batches of 1.5-4 waves gain (scripts/gpu_reserve_sizes.py, 3 seeds per size, trot / mixed gaits:
+    // 1536-3584 problems +2...+7 %; 1024 and >= 4096 problems -1...-6 %: in a long launch the hardest problems are over
+    // long before the end, and the rank assignment costs every CTA two L2 round trips)
+    if (p.sched && reserve_on && hard_sm > 0 && per_sm > cmpc::kHardSlots && nsm >= 2 * hard_sm && 2 * p.B > 3 * wave && p.B <= 4 * wave &&
         hard_sm * cmpc::kHardSlots <= p.B / 4) {
       p.n_hard_sm = hard_sm;
       p.n_hard = hard_sm * cmpc::kHardSlots;
@@ -237,7 +238,7 @@ struct HorizonEntry {
 // Slot 0 is the default kernel of the horizon:
 //   N <= 16: dense single-CTA kernel (cmpc_kernels.cuh); N = 10: <10, 1, MINB = 6, 1, CACHE, TC, SCHED> = factorisation
 //            sweep on the tensor cores (cmpc_tc.cuh), 6 CTAs/SM at 168 registers, reserved-SM rank assignment for
-//            batches of 1-5 waves; slot 1 = the SIMT sweep at 8 CTAs/SM (round-1 layout), slot 2 = tensor-core sweep
+//            batches of 1.5-4 waves; slot 1 = the SIMT sweep at 8 CTAs/SM (round-1 layout), slot 2 = tensor-core sweep
 //            at 8 CTAs/SM / 128 registers (scripts/gpu_tc_exp.py, gpu_carve_exp.py, gpu_reserve_exp.py);
 //   N >= 20: stage-wise Riccati kernel (cmpc_riccati.cuh), measured on B200 against the dense / cluster
 //            kernels: N=20 1.5x at 16384 problems (equal at 4096), N=30 2.25x (config 4), N=40 3.4x, N=60 5.2x
@@ -364,7 +365,7 @@ int schedule_batch(cmpc_handle* h, cmpc::SolveParams& p, cudaStream_t s) {
                       h->d_order + p.slot0, p.B));
   h->launches.fetch_add(2);
   p.order = h->d_order + p.slot0;
-  p.sched = h->d_sched + (size_t)cmpc::kSchedInts * hist_slot;   // used by the dense kernels for batches of more than one wave
+  p.sched = h->d_sched + (size_t)cmpc::kSchedInts * hist_slot;   // used by the dense kernels for batches of 1.5-4 waves
   return CMPC_OK;
 }
 

@@ -80,7 +80,7 @@ struct SolveParams {
   float rho_adapt_floor;              // kRhoAdaptFloor
   long long* dbg_clk;                 // debug: phase timestamps of CTA 0 (nullptr in production)
   long long* dbg_tl;                  // debug: [B][4] start ns, end ns, SM id, iterations of every CTA (nullptr in production)
-  // batches of more than one wave: CTAs take their launch-order rank when they start; the first n_hard ranks
+  // batches of 1.5-4 waves: CTAs take their launch-order rank when they start; the first n_hard ranks
   // (the hardest by the LPT score) go to kHardSlots CTAs on each of n_hard_sm reserved SMs, whose other CTAs
   // wait until those problems are done (see "work distribution" in solve_kernel)
   int32_t* sched;                     // kSchedInts ints of scheduling state, all zero between launches

@@ -215,7 +215,7 @@ def test_warm_start_semantics():
 
 @pytest.mark.timeout(300)
 def test_reserved_sm_rank_assignment_is_transparent():
-    """Batches of 1-5 waves of CTAs take their launch rank when a CTA starts, the hardest ranks on
+    """Batches of 1.5-4 waves of CTAs take their launch rank when a CTA starts, the hardest ranks on
     reserved SMs (solve_kernel "work distribution"): results must be those of the plain one-CTA-per-rank
     launch - compared with the same problems solved in sub-batches of less than one wave - whatever the
     batch size, also when two such launches share the device (staged host path: two chunks, two streams)
@@ -225,8 +225,8 @@ def test_reserved_sm_rank_assignment_is_transparent():
         return np.concatenate([x["U"] for x in parts]), np.concatenate([x["iters"] for x in parts])
     big = synthetic_batch(5921, N=10, seed=0)
     big_U, big_it = in_sub_batches(big)
-    pb = big.slice(0, 4096)
-    ref_U, ref_it = big_U[:4096], big_it[:4096]
+    pb = big.slice(0, 3000)                               # inside the range that uses the rank assignment
+    ref_U, ref_it = big_U[:3000], big_it[:3000]
     mpc = pkg.BatchedMPC(N=10, max_batch=pb.B, warm_mode=0)
     args = dev_args(pb)
     for _ in range(3):                                   # repeated launches on the same scheduling state
@@ -234,15 +234,16 @@ def test_reserved_sm_rank_assignment_is_transparent():
         torch.cuda.synchronize()
         assert np.array_equal(U.cpu().numpy().astype(np.float64), ref_U)
         assert np.array_equal(st.iters.cpu().numpy(), ref_it)
-    for B in (888, 889, 1185, 2048, 4440, 4441, 5920, 5921):   # around the one- and five-wave limits at 6 / 8 CTAs per SM
+    for B in (888, 889, 1332, 1333, 2048, 3552, 3553, 4736, 4737):   # around the 1.5- and 4-wave limits at 6 / 8 CTAs per SM
         d = gpu_solve(big.slice(0, B), warm_mode=0)
         assert np.array_equal(d["U"], big_U[:B]) and np.array_equal(d["iters"], big_it[:B]), B
         assert np.all(d["status"] == 1)
-    hin = [torch.from_numpy(a).pin_memory().numpy() for a in pb.f32()]
-    m2 = pkg.BatchedMPC(N=10, max_batch=pb.B, warm_mode=0, host_zero_copy=0)
-    for _ in range(2):
-        Uh, Xh, sh = m2.solve_host(*hin)
-        assert np.array_equal(Uh.astype(np.float64), ref_U) and np.array_equal(sh.iters, ref_it)
+    for n in (3000, 4096):                                # two chunks of 1500 / 2048 on two streams, both in the range
+        hin = [torch.from_numpy(a).pin_memory().numpy() for a in big.slice(0, n).f32()]
+        m2 = pkg.BatchedMPC(N=10, max_batch=n, warm_mode=0, host_zero_copy=0)
+        for _ in range(2):
+            Uh, Xh, sh = m2.solve_host(*hin)
+            assert np.array_equal(Uh.astype(np.float64), big_U[:n]) and np.array_equal(sh.iters, big_it[:n]), n
 
 
 def test_host_path_matches_device_path_and_sharding():

@@ -373,7 +373,7 @@ int schedule_batch(cmpc_handle* h, cmpc::SolveParams& p, cudaStream_t s) {
 // (device memory, or page-locked host memory mapped into the device's address space)
 int solve_device(cmpc_handle* h, int B, int slot0, const float* x0, const float* r, const uint8_t* mask,
                  const float* x_des, const float* mu, float* U, float* X, int32_t* iters, float* pri_res,
-                 float* dua_res, int32_t* status, cudaStream_t s, bool timed) {
+                 float* dua_res, int32_t* status, cudaStream_t s, bool timed, bool plain_launch = false) {
   const int N = h->cfg.N, NK = h->NK;
   cmpc::SolveParams p{};
   fill_solve_params(h, p);
@@ -399,6 +399,7 @@ int solve_device(cmpc_handle* h, int B, int slot0, const float* x0, const float*
   }
   int rc = schedule_batch(h, p, s);
   if (rc) return rc;
+  if (plain_launch) p.sched = nullptr;   // chunked host path: the launch shares the device with its sibling chunk
   static const bool dbg = std::getenv("CMPC_DEBUG_CLOCKS") != nullptr;   // developer aid, synchronous
   if (dbg) { CUDA_TRY(cudaMalloc(&p.dbg_clk, 32 * sizeof(long long))); CUDA_TRY(cudaMemset(p.dbg_clk, 0, 32 * sizeof(long long))); }
   static const char* tl_path = std::getenv("CMPC_DEBUG_TIMELINE");          // developer aid, synchronous
@@ -1052,7 +1053,8 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, c
                       (const uint8_t*)(din + La.mask), (const float*)(din + La.xdes),
                       (const float*)(din + La.mu), (float*)(dout + La.U),
                       X ? (float*)(dout + La.X) : nullptr, (int32_t*)(dout + La.iters),
-                      (float*)(dout + La.pri), (float*)(dout + La.dua), (int32_t*)(dout + La.status), s, false);
+                      (float*)(dout + La.pri), (float*)(dout + La.dua), (int32_t*)(dout + La.status), s, false,
+                      nchunk > 1);
     if (rc) return rc;
     if (out_pinned) {
       CUDA_TRY(cudaMemcpyAsync(U + (size_t)lo * nu, dout + La.U, (size_t)n * nu * 4, cudaMemcpyDeviceToHost, s));

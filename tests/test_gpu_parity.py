@@ -238,12 +238,23 @@ def test_reserved_sm_rank_assignment_is_transparent():
         d = gpu_solve(big.slice(0, B), warm_mode=0)
         assert np.array_equal(d["U"], big_U[:B]) and np.array_equal(d["iters"], big_it[:B]), B
         assert np.all(d["status"] == 1)
-    for n in (3000, 4096):                                # two chunks of 1500 / 2048 on two streams, both in the range
-        hin = [torch.from_numpy(a).pin_memory().numpy() for a in big.slice(0, n).f32()]
-        m2 = pkg.BatchedMPC(N=10, max_batch=n, warm_mode=0, host_zero_copy=0)
-        for _ in range(2):
-            Uh, Xh, sh = m2.solve_host(*hin)
-            assert np.array_equal(Uh.astype(np.float64), big_U[:n]) and np.array_equal(sh.iters, big_it[:n]), n
+    # two launches of one handle on two streams (disjoint slot ranges), both in the range: they share the SMs, each
+    # with its own reserved ones (the first version of the scheme could hang here)
+    m2 = pkg.BatchedMPC(N=10, max_batch=4096, warm_mode=0)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    a1, a2 = dev_args(big.slice(0, 2048)), dev_args(big.slice(2048, 4096))
+    torch.cuda.synchronize()
+    for _ in range(3):
+        U1, _, st1 = m2.solve(*a1, slot0=0, stream=s1.cuda_stream)
+        U2, _, st2 = m2.solve(*a2, slot0=2048, stream=s2.cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(np.concatenate([U1.cpu().numpy(), U2.cpu().numpy()]).astype(np.float64), big_U[:4096])
+        assert np.array_equal(np.concatenate([st1.iters.cpu().numpy(), st2.iters.cpu().numpy()]), big_it[:4096])
+    # the chunked host path (pageable buffers, host_zero_copy = 0) launches its chunks plainly
+    hin = [torch.from_numpy(a).pin_memory().numpy() for a in big.slice(0, 4096).f32()]
+    m3 = pkg.BatchedMPC(N=10, max_batch=4096, warm_mode=0, host_zero_copy=0)
+    Uh, Xh, sh = m3.solve_host(*hin)
+    assert np.array_equal(Uh.astype(np.float64), big_U[:4096]) and np.array_equal(sh.iters, big_it[:4096])
 
 
 def test_host_path_matches_device_path_and_sharding():

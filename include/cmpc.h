@@ -42,7 +42,7 @@ extern "C" {
 #endif
 
 #define CMPC_VERSION_MAJOR 0
-#define CMPC_VERSION_MINOR 2
+#define CMPC_VERSION_MINOR 3
 
 enum {
   CMPC_OK = 0,
@@ -141,6 +141,18 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0,
                     const float* x0, const float* r, const uint8_t* mask, const float* x_des,
                     const float* mu, float* U, float* X, int32_t* iters, float* pri_res,
                     float* dua_res, int32_t* status);
+
+/* Asynchronous form of cmpc_solve_host for page-locked buffers (cfg.host_zero_copy = 1): the batch is
+ * enqueued on the handle's host-path stream and the call returns with a ticket; the buffers belong to the
+ * library until cmpc_host_wait(h, ticket) returns.  Submissions are processed in order, so a caller with a
+ * stream of batches double-buffers: submit batch k+1, wait for batch k - the host work of one call then
+ * overlaps the device work of the other.  CMPC_ERR_UNSUPPORTED for pageable buffers (use cmpc_solve_host).
+ * (No counterpart in the reference, whose solve is synchronous: src/mpc.py:247.) */
+int cmpc_solve_host_async(cmpc_handle* h, int32_t B, int32_t slot0,
+                          const float* x0, const float* r, const uint8_t* mask, const float* x_des,
+                          const float* mu, float* U, float* X, int32_t* iters, float* pri_res,
+                          float* dua_res, int32_t* status, int32_t* ticket);
+int cmpc_host_wait(cmpc_handle* h, int32_t ticket);
 
 /* Exports the dense condensed QP  min 1/2 u'Hu + g'u  over all 12N forces
  * (H [B,12N,12N], g [B,12N]; rows/columns of swing legs are zero), i.e. what CasADi

@@ -9,7 +9,7 @@ from . import _capi                                             # noqa: F401
 from ._capi import CmpcError                                    # noqa: F401
 from .solver import BatchedMPC, MPC, SolveStats                 # noqa: F401
 
-__version__ = "0.2.0"
+__version__ = "0.3.0"
 from . import sharding                                           # noqa: F401,E402
 from .rollout import ClosedLoopRollout                           # noqa: F401,E402
 from . import logexport                                          # noqa: F401,E402

@@ -24,6 +24,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 #: every symbol include/cmpc.h declares
 SYMBOLS = ("cmpc_default_config", "cmpc_create", "cmpc_destroy", "cmpc_solve", "cmpc_solve_host",
+           "cmpc_solve_host_async", "cmpc_host_wait",
            "cmpc_condense", "cmpc_reset_warm", "cmpc_get_warm", "cmpc_set_warm",
            "cmpc_launch_count", "cmpc_supported_horizons", "cmpc_version", "cmpc_last_error",
            "cmpc_assemble", "cmpc_plant_step", "cmpc_fp32_peak", "cmpc_leg_torques", "cmpc_last_kernel_ms", "cmpc_get_cache_meta", "cmpc_accumulate_stats",
@@ -102,6 +103,9 @@ def lib() -> C.CDLL:
                              f32p, i32p, vp]
     L.cmpc_solve_host.argtypes = [vp, i32, i32, f32p, f32p, u8p, f32p, f32p, f32p, f32p, i32p,
                                   f32p, f32p, i32p]
+    L.cmpc_solve_host_async.argtypes = [vp, i32, i32, f32p, f32p, u8p, f32p, f32p, f32p, f32p, i32p,
+                                        f32p, f32p, i32p, i32p]
+    L.cmpc_host_wait.argtypes = [vp, i32]
     L.cmpc_condense.argtypes = [vp, i32, f32p, f32p, u8p, f32p, f32p, f32p, vp]
     L.cmpc_reset_warm.argtypes = [vp, u8p]
     L.cmpc_reset_warm_async.argtypes = [vp, i32, i32, u8p, vp]

@@ -81,6 +81,8 @@ struct Staging {
   size_t in_bytes = 0, out_bytes = 0;
   cudaStream_t streams[2] = {nullptr, nullptr};
   int cap = 0;             // problems
+  cudaEvent_t done[8] = {};   // cmpc_solve_host_async: completion of the last 8 submissions
+  int32_t next_ticket = 0;
 };
 
 }  // namespace
@@ -698,6 +700,8 @@ int cmpc_destroy(cmpc_handle* h) {
   cudaFree(h->st.d_out);
   for (auto& s : h->st.streams)
     if (s) cudaStreamDestroy(s);
+  for (auto& e : h->st.done)
+    if (e) cudaEventDestroy(e);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
@@ -967,6 +971,33 @@ bool is_pinned(const void* ptr, void** dev = nullptr) {
 }
 }  // namespace
 
+namespace {
+// Page-locked caller buffers: one launch over the whole batch, every CTA pulls its own
+// ~1.1 KB record over PCIe and pushes its results back, so the transfers overlap the
+// solve CTA by CTA and no copy is ever enqueued.  All accesses of the kernel to these
+// buffers are coalesced and touch every byte once.  Returns 1 when the batch was enqueued on
+// the host-path stream, 0 when the buffers are not all page-locked, < 0 on error.
+int enqueue_zero_copy(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, const float* r,
+                      const uint8_t* mask, const float* x_des, const float* mu, float* U, float* X,
+                      int32_t* iters, float* pri_res, float* dua_res, int32_t* status) {
+  Staging& st = h->st;
+  void *dx0, *dr, *dmask, *dxd, *dmu, *dU, *dX, *dit, *dpr, *ddu, *dst;
+  const bool ok = is_pinned(x0, &dx0) && is_pinned(r, &dr) && is_pinned(mask, &dmask) &&
+                  is_pinned(x_des, &dxd) && is_pinned(mu, &dmu) && is_pinned(U, &dU) &&
+                  is_pinned(X, &dX) && is_pinned(iters, &dit) && is_pinned(pri_res, &dpr) &&
+                  is_pinned(dua_res, &ddu) && is_pinned(status, &dst);
+  if (!(ok && dx0 && dr && dmask && dxd && dmu && dU)) return 0;
+  if (!st.streams[0]) {
+    if (cudaStreamCreateWithFlags(&st.streams[0], cudaStreamNonBlocking) != cudaSuccess)
+      return fail(CMPC_ERR_CUDA, "stream creation failed");
+  }
+  const int rc = solve_device(h, B, slot0, (const float*)dx0, (const float*)dr, (const uint8_t*)dmask,
+                              (const float*)dxd, (const float*)dmu, (float*)dU, (float*)dX, (int32_t*)dit,
+                              (float*)dpr, (float*)ddu, (int32_t*)dst, st.streams[0], false);
+  return rc ? (rc < 0 ? rc : -rc) : 1;
+}
+}  // namespace
+
 int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, const float* r,
                     const uint8_t* mask, const float* x_des, const float* mu, float* U, float* X,
                     int32_t* iters, float* pri_res, float* dua_res, int32_t* status) {
@@ -978,21 +1009,9 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, c
   const int N = h->cfg.N;
   Staging& st = h->st;
   if (h->cfg.host_zero_copy) {
-    // Page-locked caller buffers: one launch over the whole batch, every CTA pulls its own
-    // ~1.1 KB record over PCIe and pushes its results back, so the transfers overlap the
-    // solve CTA by CTA and no copy is ever enqueued.  All accesses of the kernel to these
-    // buffers are coalesced and touch every byte once.
-    void *dx0, *dr, *dmask, *dxd, *dmu, *dU, *dX, *dit, *dpr, *ddu, *dst;
-    const bool ok = is_pinned(x0, &dx0) && is_pinned(r, &dr) && is_pinned(mask, &dmask) &&
-                    is_pinned(x_des, &dxd) && is_pinned(mu, &dmu) && is_pinned(U, &dU) &&
-                    is_pinned(X, &dX) && is_pinned(iters, &dit) && is_pinned(pri_res, &dpr) &&
-                    is_pinned(dua_res, &ddu) && is_pinned(status, &dst);
-    if (ok && dx0 && dr && dmask && dxd && dmu && dU) {
-      if (!st.streams[0]) CUDA_TRY(cudaStreamCreateWithFlags(&st.streams[0], cudaStreamNonBlocking));
-      rc = solve_device(h, B, slot0, (const float*)dx0, (const float*)dr, (const uint8_t*)dmask,
-                        (const float*)dxd, (const float*)dmu, (float*)dU, (float*)dX, (int32_t*)dit,
-                        (float*)dpr, (float*)ddu, (int32_t*)dst, st.streams[0], false);
-      if (rc) return rc;
+    rc = enqueue_zero_copy(h, B, slot0, x0, r, mask, x_des, mu, U, X, iters, pri_res, dua_res, status);
+    if (rc < 0) return rc;
+    if (rc == 1) {
       CUDA_TRY(cudaStreamSynchronize(st.streams[0]));
       return CMPC_OK;
     }
@@ -1081,6 +1100,45 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, c
     if (dua_res) std::memcpy(dua_res + lo, hout + La.dua, (size_t)n * 4);
     if (status) std::memcpy(status + lo, hout + La.status, (size_t)n * 4);
   }
+  return CMPC_OK;
+}
+
+
+int cmpc_solve_host_async(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, const float* r,
+                          const uint8_t* mask, const float* x_des, const float* mu, float* U, float* X,
+                          int32_t* iters, float* pri_res, float* dua_res, int32_t* status, int32_t* ticket) {
+  int rc = check_batch(h, B, slot0);
+  if (rc) return rc;
+  if (!ticket) return fail(CMPC_ERR_INVALID, "null ticket pointer");
+  if (!x0 || !r || !mask || !x_des || !mu || !U) return fail(CMPC_ERR_INVALID, "null input/output pointer");
+  if (!h->cfg.host_zero_copy) return fail(CMPC_ERR_UNSUPPORTED, "cmpc_solve_host_async needs cfg.host_zero_copy");
+  DEVICE_GUARD(h);
+  Staging& st = h->st;
+  if (B > 0) {
+    rc = enqueue_zero_copy(h, B, slot0, x0, r, mask, x_des, mu, U, X, iters, pri_res, dua_res, status);
+    if (rc < 0) return rc;
+    if (rc == 0) return fail(CMPC_ERR_UNSUPPORTED, "cmpc_solve_host_async needs page-locked buffers (use cmpc_solve_host)");
+  } else if (!st.streams[0]) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&st.streams[0], cudaStreamNonBlocking));
+  }
+  const int32_t t = st.next_ticket++;
+  cudaEvent_t& ev = st.done[t & 7];
+  if (!ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(ev, st.streams[0]));
+  *ticket = t;
+  return CMPC_OK;
+}
+
+int cmpc_host_wait(cmpc_handle* h, int32_t ticket) {
+  if (!h) return fail(CMPC_ERR_INVALID, "null handle");
+  Staging& st = h->st;
+  if (ticket < 0 || ticket >= st.next_ticket) return fail(CMPC_ERR_INVALID, "unknown ticket %d", ticket);
+  DEVICE_GUARD(h);
+  if (st.next_ticket - ticket > 8) {     // its event was reused: submissions complete in order, wait for the oldest kept
+    CUDA_TRY(cudaEventSynchronize(st.done[st.next_ticket & 7]));
+    return CMPC_OK;
+  }
+  CUDA_TRY(cudaEventSynchronize(st.done[ticket & 7]));
   return CMPC_OK;
 }
 

@@ -150,6 +150,27 @@ class BatchedMPC:
             _np_ptr(U), _np_ptr(X), _np_ptr(iters), _np_ptr(pri), _np_ptr(dua), _np_ptr(status)))
         return U, X, SolveStats(iters, pri, dua, status)
 
+    def solve_host_async(self, x0, r, mask, x_des, mu, out, slot0=0):
+        """``cmpc_solve_host_async``: page-locked numpy arrays in and out (``out`` = (U, X or None, iters,
+        pri_res, dua_res, status), all page-locked); returns a ticket.  The arrays belong to the library until
+        ``host_wait(ticket)`` returns; submissions are processed in order (double-buffer to overlap the host
+        work of one batch with the device work of the previous one)."""
+        B = x0.shape[0]
+        for a, dt in ((x0, np.float32), (r, np.float32), (mask, np.uint8), (x_des, np.float32),
+                      (mu, np.float32)):
+            if a.dtype != dt or not a.flags.c_contiguous:
+                raise ValueError("solve_host_async needs C-contiguous fp32 / uint8 arrays")
+        U, X, iters, pri, dua, status = out
+        ticket = C.c_int32(-1)
+        _capi.check(_capi.lib().cmpc_solve_host_async(
+            self._h, B, slot0, _np_ptr(x0), _np_ptr(r), _np_ptr(mask), _np_ptr(x_des), _np_ptr(mu),
+            _np_ptr(U), _np_ptr(X), _np_ptr(iters), _np_ptr(pri), _np_ptr(dua), _np_ptr(status),
+            C.byref(ticket)))
+        return int(ticket.value)
+
+    def host_wait(self, ticket):
+        _capi.check(_capi.lib().cmpc_host_wait(self._h, int(ticket)))
+
     # -- warm-start state ---------------------------------------------------------------
     def reset_warm_async(self, B=None, slot0=0, slot_mask=None, stream=None):
         """Stream-ordered reset of slots [slot0, slot0+B); `slot_mask` = uint8 device tensor of B bytes."""

@@ -47,7 +47,7 @@ def test_default_config_matches_reference_constants():
 def test_supported_horizons_and_version():
     hs = _capi.supported_horizons()
     assert 10 in hs and 30 in hs and hs == sorted(hs)
-    assert _capi.lib().cmpc_version() == 2
+    assert _capi.lib().cmpc_version() == 3
 
 
 def test_any_horizon_maps_to_a_compiled_kernel():

@@ -257,6 +257,35 @@ def test_reserved_sm_rank_assignment_is_transparent():
     assert np.array_equal(Uh.astype(np.float64), big_U[:4096]) and np.array_equal(sh.iters, big_it[:4096])
 
 
+def test_async_host_path_double_buffered():
+    """cmpc_solve_host_async / cmpc_host_wait: two batches in flight on page-locked buffers give the
+    results of the blocking call; pageable buffers are refused."""
+    pbs = [synthetic_batch(1500, N=10, gaits=GAIT_NAMES, seed=s) for s in (21, 22, 23)]
+    refs = [gpu_solve(pb, warm_mode=0) for pb in pbs]
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    zeros = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()
+    mpc = pkg.BatchedMPC(N=10, max_batch=1500, warm_mode=0)
+    ins = [[pin(a) for a in pb.f32()] for pb in pbs]
+    outs = [(zeros((1500, 10, 12), torch.float32), zeros((1500, 11, 13), torch.float32), zeros((1500,), torch.int32),
+             zeros((1500,), torch.float32), zeros((1500,), torch.float32), zeros((1500,), torch.int32)) for _ in pbs]
+    tickets = [mpc.solve_host_async(*ins[k], out=outs[k]) for k in range(3)]       # three submissions in flight
+    assert tickets == [0, 1, 2]
+    for k in (2, 0, 1):                                                              # any waiting order
+        mpc.host_wait(tickets[k])
+        assert np.array_equal(outs[k][0].astype(np.float64), refs[k]["U"])
+        assert np.array_equal(outs[k][1].astype(np.float64), refs[k]["X"])
+        assert np.array_equal(outs[k][2], refs[k]["iters"]) and np.array_equal(outs[k][5], refs[k]["status"])
+    for _ in range(12):                                                              # more submissions than kept events
+        t = mpc.solve_host_async(*ins[0], out=outs[0])
+    mpc.host_wait(3)
+    mpc.host_wait(t)
+    assert np.array_equal(outs[0][0].astype(np.float64), refs[0]["U"])
+    with pytest.raises(pkg._capi.CmpcError):
+        mpc.solve_host_async(*pbs[0].f32(), out=outs[0])                             # pageable inputs
+    with pytest.raises(pkg._capi.CmpcError):
+        mpc.host_wait(t + 1)
+
+
 def test_host_path_matches_device_path_and_sharding():
     """cmpc_solve_host (pinned staging, chunked streams) returns bit-identical results to
     cmpc_solve, and solving two half batches equals solving the whole batch (problems are

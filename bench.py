@@ -400,8 +400,8 @@ def run_ours(args):
     e2e_block_s = time.perf_counter() - t0
     bench.barrier()
     # the same steps double-buffered through cmpc_solve_host_async / cmpc_host_wait: step k+1 is submitted
-    # (its own page-locked input and output buffers) before step k is waited for, so the host side of one
-    # call overlaps the device side of the other; every step still moves its inputs and results over PCIe
+    # (its own page-locked input and output buffers) before step k is waited for, so its host-to-device copies
+    # and the host side of the call overlap the solve of step k; every step moves its inputs and results over PCIe
     hin2 = [torch.from_numpy(a).clone().pin_memory().numpy() for a in hin]
     hout2 = (pin((B, N, 12), torch.float32), None, pin((B,), torch.int32),
              pin((B,), torch.float32), pin((B,), torch.float32), pin((B,), torch.int32))
@@ -546,9 +546,11 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": out_bytes,
                 "blocking_value": total / e2e_block_s_max,
-                "api": ("cmpc_solve_host_async + cmpc_host_wait, two steps in flight (each with its own page-locked "
-                        "input and output buffers, read / written in place by the solve kernel over PCIe); "
-                        "blocking_value = the same steps through the blocking cmpc_solve_host"
+                "api": ("cmpc_solve_host_async + cmpc_host_wait, two steps in flight, each with its own page-locked "
+                        "input and output buffers: the inputs of step k+1 are copied by the copy engines "
+                        "(cudaMemcpyAsync) into a device arena while step k is solved, the results are written in "
+                        "place into the page-locked output buffers by the solve kernel; blocking_value = the same "
+                        "steps through the blocking cmpc_solve_host (kernel reads / writes host memory in place)"
                         if int(mpc.cfg.host_zero_copy) else "cmpc_solve_host, staged with chunked cudaMemcpyAsync")},
         "warm_start": {"value": total / (warm_ms_max * 1e-3), "unit": "solves/s",
                        "ms_per_step": warm_ms_max / args.steps, "mean_iters": float(warm_iters.mean()),

@@ -145,8 +145,9 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0,
 /* Asynchronous form of cmpc_solve_host for page-locked buffers (cfg.host_zero_copy = 1): the batch is
  * enqueued on the handle's host-path stream and the call returns with a ticket; the buffers belong to the
  * library until cmpc_host_wait(h, ticket) returns.  Submissions are processed in order, so a caller with a
- * stream of batches double-buffers: submit batch k+1, wait for batch k - the host work of one call then
- * overlaps the device work of the other.  CMPC_ERR_UNSUPPORTED for pageable buffers (use cmpc_solve_host).
+ * stream of batches double-buffers: submit batch k+1, wait for batch k.  The inputs of a submission are copied
+ * by the copy engines into one of two device arenas while the previous submission is solved, the results are
+ * written in place by the solve kernel.  CMPC_ERR_UNSUPPORTED for pageable buffers (use cmpc_solve_host).
  * (No counterpart in the reference, whose solve is synchronous: src/mpc.py:247.) */
 int cmpc_solve_host_async(cmpc_handle* h, int32_t B, int32_t slot0,
                           const float* x0, const float* r, const uint8_t* mask, const float* x_des,

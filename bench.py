@@ -402,25 +402,30 @@ def run_ours(args):
     # the same steps double-buffered through cmpc_solve_host_async / cmpc_host_wait: step k+1 is submitted
     # (its own page-locked input and output buffers) before step k is waited for, so its host-to-device copies
     # and the host side of the call overlap the solve of step k; every step moves its inputs and results over PCIe
-    hin2 = [torch.from_numpy(a).clone().pin_memory().numpy() for a in hin]
-    hout2 = (pin((B, N, 12), torch.float32), None, pin((B,), torch.int32),
-             pin((B,), torch.float32), pin((B,), torch.float32), pin((B,), torch.int32))
-    bufs = ((hin, hout), (hin2, hout2))
+    bufs = [(hin, hout)]
+    for _ in range(2):        # three buffer sets: the host runs up to two submissions ahead of the wait
+        bufs.append(([torch.from_numpy(a).clone().pin_memory().numpy() for a in hin],
+                     (pin((B, N, 12), torch.float32), None, pin((B,), torch.int32),
+                      pin((B,), torch.float32), pin((B,), torch.float32), pin((B,), torch.int32))))
     e2e_s = e2e_block_s
     if int(mpc.cfg.host_zero_copy):
         for k in range(3):
-            mpc.host_wait(mpc.solve_host_async(*bufs[k % 2][0], out=bufs[k % 2][1]))
-        bench.barrier()
-        t0 = time.perf_counter()
-        prev = None
-        for k in range(args.steps):
-            tk = mpc.solve_host_async(*bufs[k % 2][0], out=bufs[k % 2][1])
-            if prev is not None:
-                mpc.host_wait(prev)
-            prev = tk
-        mpc.host_wait(prev)
-        e2e_s = time.perf_counter() - t0
-        assert np.array_equal(hout[0], hout2[0]) and np.array_equal(hout[2], hout2[2])
+            mpc.host_wait(mpc.solve_host_async(*bufs[k][0], out=bufs[k][1]))
+        reps = []
+        for _ in range(5):    # the K-step loop lasts a few ms and one nvidia-smi sample (every 100 ms, driver lock)
+            bench.barrier()   # inside it costs up to 30 %: median of 5 repetitions of the K steps
+            t0 = time.perf_counter()
+            tickets = []
+            for k in range(args.steps):
+                tickets.append(mpc.solve_host_async(*bufs[k % 3][0], out=bufs[k % 3][1]))
+                if k >= 2:
+                    mpc.host_wait(tickets[k - 2])
+            for tk in tickets[-2:]:
+                mpc.host_wait(tk)
+            reps.append(time.perf_counter() - t0)
+        e2e_s = statistics.median(reps)
+        for q in bufs[1:]:
+            assert np.array_equal(hout[0], q[1][0]) and np.array_equal(hout[2], q[1][2])
         bench.barrier()
     clocks = sampler.stop() if rank == 0 else None
 
@@ -546,10 +551,10 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": out_bytes,
                 "blocking_value": total / e2e_block_s_max,
-                "api": ("cmpc_solve_host_async + cmpc_host_wait, two steps in flight, each with its own page-locked "
+                "api": ("cmpc_solve_host_async + cmpc_host_wait, up to three steps in flight, each with its own page-locked "
                         "input and output buffers: the inputs of step k+1 are copied by the copy engines "
                         "(cudaMemcpyAsync) into a device arena while step k is solved, the results are written in "
-                        "place into the page-locked output buffers by the solve kernel; blocking_value = the same "
+                        "place into the page-locked output buffers by the solve kernel (median of 5 repetitions of the K steps); blocking_value = the same "
                         "steps through the blocking cmpc_solve_host (kernel reads / writes host memory in place)"
                         if int(mpc.cfg.host_zero_copy) else "cmpc_solve_host, staged with chunked cudaMemcpyAsync")},
         "warm_start": {"value": total / (warm_ms_max * 1e-3), "unit": "solves/s",

@@ -407,17 +407,19 @@ def run_ours(args):
         bufs.append(([torch.from_numpy(a).clone().pin_memory().numpy() for a in hin],
                      (pin((B, N, 12), torch.float32), None, pin((B,), torch.int32),
                       pin((B,), torch.float32), pin((B,), torch.float32), pin((B,), torch.int32))))
-    e2e_s = e2e_block_s
+    e2e_s, reps, submit_us = e2e_block_s, [], [0.0]
     if int(mpc.cfg.host_zero_copy):
         for k in range(3):
             mpc.host_wait(mpc.solve_host_async(*bufs[k][0], out=bufs[k][1]))
-        reps = []
+        submit_us = []
         for _ in range(5):    # the K-step loop lasts a few ms and one nvidia-smi sample (every 100 ms, driver lock)
             bench.barrier()   # inside it costs up to 30 %: median of 5 repetitions of the K steps
             t0 = time.perf_counter()
             tickets = []
             for k in range(args.steps):
+                h0 = time.perf_counter()
                 tickets.append(mpc.solve_host_async(*bufs[k % 3][0], out=bufs[k % 3][1]))
+                submit_us.append((time.perf_counter() - h0) * 1e6)
                 if k >= 2:
                     mpc.host_wait(tickets[k - 2])
             for tk in tickets[-2:]:
@@ -551,6 +553,9 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": out_bytes,
                 "blocking_value": total / e2e_block_s_max,
+                "rank0_ms_per_step_of_the_5_repetitions": [r_ / args.steps * 1e3 for r_ in reps],
+                "rank0_host_us_per_submission": {"p50": float(np.percentile(submit_us, 50)), "p95": float(np.percentile(submit_us, 95)),
+                                                 "max": float(np.max(submit_us))},
                 "api": ("cmpc_solve_host_async + cmpc_host_wait, up to three steps in flight, each with its own page-locked "
                         "input and output buffers: the inputs of step k+1 are copied by the copy engines "
                         "(cudaMemcpyAsync) into a device arena while step k is solved, the results are written in "

@@ -80,6 +80,8 @@ struct Staging {
   char* d_out = nullptr;
   size_t in_bytes = 0, out_bytes = 0;
   cudaStream_t streams[2] = {nullptr, nullptr};
+  cudaStream_t copy2 = nullptr;   // second copy stream of the async path (a second copy engine)
+  cudaEvent_t h2d2[2] = {};
   int cap = 0;             // problems
   cudaEvent_t done[8] = {};   // cmpc_solve_host_async: completion of the last 8 submissions
   int32_t next_ticket = 0;
@@ -707,6 +709,9 @@ int cmpc_destroy(cmpc_handle* h) {
     if (e) cudaEventDestroy(e);
   for (auto& e : h->st.h2d)
     if (e) cudaEventDestroy(e);
+  for (auto& e : h->st.h2d2)
+    if (e) cudaEventDestroy(e);
+  if (h->st.copy2) cudaStreamDestroy(h->st.copy2);
   for (auto& q : h->st.d_async_in) cudaFree(q);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1145,14 +1150,28 @@ int cmpc_solve_host_async(cmpc_handle* h, int32_t B, int32_t slot0, const float*
     const int a = t & 1;
     char* din = st.d_async_in[a];
     cudaStream_t cs = st.streams[1], ks = st.streams[0];
-    if (t >= 2) CUDA_TRY(cudaStreamWaitEvent(cs, st.done[(t - 2) & 7], 0));   // the solve that read this arena last
-    CUDA_TRY(cudaMemcpyAsync(din + L.x0, x0, (size_t)B * 13 * 4, cudaMemcpyHostToDevice, cs));
+    // two copy streams (two copy engines): x_des on one, the rest on the other
+    static const bool two_engines = std::getenv("CMPC_ASYNC_ONE_COPY_STREAM") == nullptr;   // experiment switch
+    if (!st.copy2) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&st.copy2, cudaStreamNonBlocking));
+      for (auto& e : st.h2d2) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaStream_t cs2 = two_engines ? st.copy2 : cs;
+    if (t >= 2) {   // the solve that read this arena last
+      CUDA_TRY(cudaStreamWaitEvent(cs, st.done[(t - 2) & 7], 0));
+      if (two_engines) CUDA_TRY(cudaStreamWaitEvent(cs2, st.done[(t - 2) & 7], 0));
+    }
+    CUDA_TRY(cudaMemcpyAsync(din + L.xdes, x_des, (size_t)B * 13 * (N + 1) * 4, cudaMemcpyHostToDevice, cs2));
     CUDA_TRY(cudaMemcpyAsync(din + L.r, r, (size_t)B * 12 * N * 4, cudaMemcpyHostToDevice, cs));
-    CUDA_TRY(cudaMemcpyAsync(din + L.xdes, x_des, (size_t)B * 13 * (N + 1) * 4, cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(cudaMemcpyAsync(din + L.x0, x0, (size_t)B * 13 * 4, cudaMemcpyHostToDevice, cs));
     CUDA_TRY(cudaMemcpyAsync(din + L.mu, mu, (size_t)B * 4, cudaMemcpyHostToDevice, cs));
     CUDA_TRY(cudaMemcpyAsync(din + L.mask, mask, (size_t)B * N, cudaMemcpyHostToDevice, cs));
     CUDA_TRY(cudaEventRecord(st.h2d[a], cs));
     CUDA_TRY(cudaStreamWaitEvent(ks, st.h2d[a], 0));
+    if (two_engines) {
+      CUDA_TRY(cudaEventRecord(st.h2d2[a], cs2));
+      CUDA_TRY(cudaStreamWaitEvent(ks, st.h2d2[a], 0));
+    }
     rc = solve_device(h, B, slot0, (const float*)(din + L.x0), (const float*)(din + L.r), (const uint8_t*)(din + L.mask),
                       (const float*)(din + L.xdes), (const float*)(din + L.mu), (float*)dU, (float*)dX, (int32_t*)dit,
                       (float*)dpr, (float*)ddu, (int32_t*)dst, ks, false);

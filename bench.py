@@ -402,6 +402,20 @@ def run_ours(args):
     # the same steps double-buffered through cmpc_solve_host_async / cmpc_host_wait: step k+1 is submitted
     # (its own page-locked input and output buffers) before step k is waited for, so its host-to-device copies
     # and the host side of the call overlap the solve of step k; every step moves its inputs and results over PCIe
+    # what this box's copy engines deliver on one step's inputs (the pipelined path is bound by it where it is
+    # slower than the solve: boxes of the pool differ, 15-60 GB/s)
+    dst = [torch.empty_like(t, device=dev) for t in pinned]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h2d_ms = []
+    for _ in range(5):
+        ev0.record()
+        for d_, t_ in zip(dst, pinned):
+            d_.copy_(t_, non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        h2d_ms.append(ev0.elapsed_time(ev1))
+    h2d_gbs = sum(t.numel() * t.element_size() for t in pinned) / (statistics.median(h2d_ms) * 1e-3) / 1e9
+    del dst
     bufs = [(hin, hout)]
     for _ in range(2):        # three buffer sets: the host runs up to two submissions ahead of the wait
         bufs.append(([torch.from_numpy(a).clone().pin_memory().numpy() for a in hin],
@@ -412,8 +426,12 @@ def run_ours(args):
         for k in range(3):
             mpc.host_wait(mpc.solve_host_async(*bufs[k][0], out=bufs[k][1]))
         submit_us = []
-        for _ in range(5):    # the K-step loop lasts a few ms and one nvidia-smi sample (every 100 ms, driver lock)
-            bench.barrier()   # inside it costs up to 30 %: median of 5 repetitions of the K steps
+        # the K-step loop lasts a few ms: one nvidia-smi sample (every 100 ms, driver lock) inside it costs up to 30 %,
+        # and the first repetitions after the blocking loop run up to 40 % slower on part of the boxes (transient
+        # of ~50 ms).  Steady state: ~1500 steps in repetitions of K (5 at least, 40 at most; the same count on
+        # every rank), median.
+        for _ in range(max(5, min(40, 1500 // max(args.steps, 1)))):
+            bench.barrier()
             t0 = time.perf_counter()
             tickets = []
             for k in range(args.steps):
@@ -553,13 +571,14 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": out_bytes,
                 "blocking_value": total / e2e_block_s_max,
-                "rank0_ms_per_step_of_the_5_repetitions": [r_ / args.steps * 1e3 for r_ in reps],
+                "rank0_ms_per_step_of_the_repetitions": [round(r_ / args.steps * 1e3, 4) for r_ in reps],
+                "rank0_h2d_copy_engine_gbs": h2d_gbs,
                 "rank0_host_us_per_submission": {"p50": float(np.percentile(submit_us, 50)), "p95": float(np.percentile(submit_us, 95)),
                                                  "max": float(np.max(submit_us))},
                 "api": ("cmpc_solve_host_async + cmpc_host_wait, up to three steps in flight, each with its own page-locked "
                         "input and output buffers: the inputs of step k+1 are copied by the copy engines "
-                        "(cudaMemcpyAsync) into a device arena while step k is solved, the results are written in "
-                        "place into the page-locked output buffers by the solve kernel (median of 5 repetitions of the K steps); blocking_value = the same "
+                        "(cudaMemcpyAsync) into a device arena while step k is solved and the results of step k are copied "
+                        "back while step k+1 is solved (median over ~1500 steps in repetitions of the K steps); blocking_value = the same "
                         "steps through the blocking cmpc_solve_host (kernel reads / writes host memory in place)"
                         if int(mpc.cfg.host_zero_copy) else "cmpc_solve_host, staged with chunked cudaMemcpyAsync")},
         "warm_start": {"value": total / (warm_ms_max * 1e-3), "unit": "solves/s",

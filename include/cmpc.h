@@ -146,8 +146,9 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0,
  * enqueued on the handle's host-path stream and the call returns with a ticket; the buffers belong to the
  * library until cmpc_host_wait(h, ticket) returns.  Submissions are processed in order, so a caller with a
  * stream of batches double-buffers: submit batch k+1, wait for batch k.  The inputs of a submission are copied
- * by the copy engines into one of two device arenas while the previous submission is solved, the results are
- * written in place by the solve kernel.  CMPC_ERR_UNSUPPORTED for pageable buffers (use cmpc_solve_host).
+ * by the copy engines into one of two device arenas while the previous submission is solved, and its results
+ * are copied back while the next one is solved; a ticket completes when the results are in the caller's
+ * buffers.  CMPC_ERR_UNSUPPORTED for pageable buffers (use cmpc_solve_host).
  * (No counterpart in the reference, whose solve is synchronous: src/mpc.py:247.) */
 int cmpc_solve_host_async(cmpc_handle* h, int32_t B, int32_t slot0,
                           const float* x0, const float* r, const uint8_t* mask, const float* x_des,

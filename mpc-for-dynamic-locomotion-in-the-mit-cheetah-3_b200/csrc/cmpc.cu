@@ -82,6 +82,9 @@ struct Staging {
   cudaStream_t streams[2] = {nullptr, nullptr};
   cudaStream_t copy2 = nullptr;   // second copy stream of the async path (a second copy engine)
   cudaEvent_t h2d2[2] = {};
+  cudaStream_t d2h = nullptr;     // results of the async path back to the caller's buffers
+  cudaEvent_t solved[2] = {};
+  char* d_async_out[2] = {nullptr, nullptr};
   int cap = 0;             // problems
   cudaEvent_t done[8] = {};   // cmpc_solve_host_async: completion of the last 8 submissions
   int32_t next_ticket = 0;
@@ -712,6 +715,10 @@ int cmpc_destroy(cmpc_handle* h) {
   for (auto& e : h->st.h2d2)
     if (e) cudaEventDestroy(e);
   if (h->st.copy2) cudaStreamDestroy(h->st.copy2);
+  if (h->st.d2h) cudaStreamDestroy(h->st.d2h);
+  for (auto& e : h->st.solved)
+    if (e) cudaEventDestroy(e);
+  for (auto& q : h->st.d_async_out) cudaFree(q);
   for (auto& q : h->st.d_async_in) cudaFree(q);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1172,10 +1179,48 @@ int cmpc_solve_host_async(cmpc_handle* h, int32_t B, int32_t slot0, const float*
       CUDA_TRY(cudaEventRecord(st.h2d2[a], cs2));
       CUDA_TRY(cudaStreamWaitEvent(ks, st.h2d2[a], 0));
     }
-    rc = solve_device(h, B, slot0, (const float*)(din + L.x0), (const float*)(din + L.r), (const uint8_t*)(din + L.mask),
-                      (const float*)(din + L.xdes), (const float*)(din + L.mu), (float*)dU, (float*)dX, (int32_t*)dit,
-                      (float*)dpr, (float*)ddu, (int32_t*)dst, ks, false);
-    if (rc) return rc;
+    // Results: into a device arena, then back with the copy engines on their own stream while the next submission
+    // is solved (CMPC_ASYNC_INPLACE_RESULTS=1: written in place into the page-locked buffers by the kernel instead;
+    // on part of the boxes of this pool that costs 0.04 ms per step)
+    static const bool engine_results = std::getenv("CMPC_ASYNC_INPLACE_RESULTS") == nullptr;
+    if (!engine_results) {
+      rc = solve_device(h, B, slot0, (const float*)(din + L.x0), (const float*)(din + L.r), (const uint8_t*)(din + L.mask),
+                        (const float*)(din + L.xdes), (const float*)(din + L.mu), (float*)dU, (float*)dX, (int32_t*)dit,
+                        (float*)dpr, (float*)ddu, (int32_t*)dst, ks, false);
+      if (rc) return rc;
+    } else {
+      const Layout Lo = make_layout(N, h->cfg.max_batch, true);
+      if (!st.d2h) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&st.d2h, cudaStreamNonBlocking));
+        for (int q = 0; q < 2; ++q) {
+          CUDA_TRY(cudaMalloc(&st.d_async_out[q], Lo.out_total));
+          CUDA_TRY(cudaEventCreateWithFlags(&st.solved[q], cudaEventDisableTiming));
+        }
+      }
+      char* dout = st.d_async_out[a];
+      if (t >= 2) CUDA_TRY(cudaStreamWaitEvent(ks, st.done[(t - 2) & 7], 0));   // its results have left this arena
+      rc = solve_device(h, B, slot0, (const float*)(din + L.x0), (const float*)(din + L.r), (const uint8_t*)(din + L.mask),
+                        (const float*)(din + L.xdes), (const float*)(din + L.mu), (float*)(dout + Lo.U),
+                        X ? (float*)(dout + Lo.X) : nullptr, iters ? (int32_t*)(dout + Lo.iters) : nullptr,
+                        pri_res ? (float*)(dout + Lo.pri) : nullptr, dua_res ? (float*)(dout + Lo.dua) : nullptr,
+                        status ? (int32_t*)(dout + Lo.status) : nullptr, ks, false);
+      if (rc) return rc;
+      CUDA_TRY(cudaEventRecord(st.solved[a], ks));
+      CUDA_TRY(cudaStreamWaitEvent(st.d2h, st.solved[a], 0));
+      CUDA_TRY(cudaMemcpyAsync(U, dout + Lo.U, (size_t)B * 12 * N * 4, cudaMemcpyDeviceToHost, st.d2h));
+      if (X) CUDA_TRY(cudaMemcpyAsync(X, dout + Lo.X, (size_t)B * 13 * (N + 1) * 4, cudaMemcpyDeviceToHost, st.d2h));
+      if (iters) CUDA_TRY(cudaMemcpyAsync(iters, dout + Lo.iters, (size_t)B * 4, cudaMemcpyDeviceToHost, st.d2h));
+      if (pri_res) CUDA_TRY(cudaMemcpyAsync(pri_res, dout + Lo.pri, (size_t)B * 4, cudaMemcpyDeviceToHost, st.d2h));
+      if (dua_res) CUDA_TRY(cudaMemcpyAsync(dua_res, dout + Lo.dua, (size_t)B * 4, cudaMemcpyDeviceToHost, st.d2h));
+      if (status) CUDA_TRY(cudaMemcpyAsync(status, dout + Lo.status, (size_t)B * 4, cudaMemcpyDeviceToHost, st.d2h));
+      // completion of this submission = its results are in the caller's buffers
+      cudaEvent_t& evd = st.done[t & 7];
+      if (!evd) CUDA_TRY(cudaEventCreateWithFlags(&evd, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventRecord(evd, st.d2h));
+      st.next_ticket++;
+      *ticket = t;
+      return CMPC_OK;
+    }
   } else if (B > 0) {
     rc = enqueue_zero_copy(h, B, slot0, x0, r, mask, x_des, mu, U, X, iters, pri_res, dua_res, status);
     if (rc < 0) return rc;
@@ -1184,7 +1229,7 @@ int cmpc_solve_host_async(cmpc_handle* h, int32_t B, int32_t slot0, const float*
   st.next_ticket++;
   cudaEvent_t& ev = st.done[t & 7];
   if (!ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  CUDA_TRY(cudaEventRecord(ev, st.streams[0]));
+  CUDA_TRY(cudaEventRecord(ev, (B == 0 && st.d2h) ? st.d2h : st.streams[0]));   // tickets complete in submission order
   *ticket = t;
   return CMPC_OK;
 }

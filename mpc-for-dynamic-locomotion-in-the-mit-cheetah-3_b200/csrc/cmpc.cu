@@ -85,6 +85,14 @@ struct Staging {
   cudaStream_t d2h = nullptr;     // results of the async path back to the caller's buffers
   cudaEvent_t solved[2] = {};
   char* d_async_out[2] = {nullptr, nullptr};
+  // result copies of the latest submission, not enqueued yet (see flush_results)
+  struct Pending {
+    bool active = false;
+    int32_t ticket = 0, B = 0;
+    int arena = 0;
+    float* U = nullptr; float* X = nullptr; int32_t* iters = nullptr;
+    float* pri = nullptr; float* dua = nullptr; int32_t* status = nullptr;
+  } pending;
   int cap = 0;             // problems
   cudaEvent_t done[8] = {};   // cmpc_solve_host_async: completion of the last 8 submissions
   int32_t next_ticket = 0;
@@ -123,6 +131,10 @@ struct cmpc_handle {
   bool timed = false;
   std::atomic<int64_t> launches{0};
 };
+
+namespace {
+int flush_results(cmpc_handle* h);   // async host path, defined with it
+}
 
 namespace {
 
@@ -708,6 +720,7 @@ int cmpc_destroy(cmpc_handle* h) {
   cudaFree(h->st.d_out);
   for (auto& s : h->st.streams)
     if (s) cudaStreamDestroy(s);
+  if (h->st.pending.active) { flush_results(h); cudaStreamSynchronize(h->st.d2h); }
   for (auto& e : h->st.done)
     if (e) cudaEventDestroy(e);
   for (auto& e : h->st.h2d)
@@ -990,6 +1003,33 @@ bool is_pinned(const void* ptr, void** dev = nullptr) {
 }  // namespace
 
 namespace {
+// Result copies of the async host path.  They are enqueued one submission late - after the NEXT submission's input
+// copies, or by cmpc_host_wait - because a copy that waits for its solve sits at the head of its hardware queue for
+// the whole solve, and when the driver maps the input-copy streams onto that queue too (it varies from process
+// to process) the next step's inputs wait behind it and the steps serialise (measured: 0.25 / 0.27 / 0.32 instead
+// of 0.23 ms per step, the delay being the copy time of whichever stream shared the queue).
+int flush_results(cmpc_handle* h) {
+  Staging& st = h->st;
+  Staging::Pending& q = st.pending;
+  if (!q.active) return CMPC_OK;
+  const int N = h->cfg.N;
+  const Layout Lo = make_layout(N, h->cfg.max_batch, true);
+  const char* dout = st.d_async_out[q.arena];
+  const size_t B = (size_t)q.B;
+  CUDA_TRY(cudaStreamWaitEvent(st.d2h, st.solved[q.arena], 0));
+  CUDA_TRY(cudaMemcpyAsync(q.U, dout + Lo.U, B * 12 * N * 4, cudaMemcpyDeviceToHost, st.d2h));
+  if (q.X) CUDA_TRY(cudaMemcpyAsync(q.X, dout + Lo.X, B * 13 * (N + 1) * 4, cudaMemcpyDeviceToHost, st.d2h));
+  if (q.iters) CUDA_TRY(cudaMemcpyAsync(q.iters, dout + Lo.iters, B * 4, cudaMemcpyDeviceToHost, st.d2h));
+  if (q.pri) CUDA_TRY(cudaMemcpyAsync(q.pri, dout + Lo.pri, B * 4, cudaMemcpyDeviceToHost, st.d2h));
+  if (q.dua) CUDA_TRY(cudaMemcpyAsync(q.dua, dout + Lo.dua, B * 4, cudaMemcpyDeviceToHost, st.d2h));
+  if (q.status) CUDA_TRY(cudaMemcpyAsync(q.status, dout + Lo.status, B * 4, cudaMemcpyDeviceToHost, st.d2h));
+  CUDA_TRY(cudaEventRecord(st.done[q.ticket & 7], st.d2h));   // a ticket completes when its results are in host memory
+  q.active = false;
+  return CMPC_OK;
+}
+}  // namespace
+
+namespace {
 // Page-locked caller buffers: one launch over the whole batch, every CTA pulls its own
 // ~1.1 KB record over PCIe and pushes its results back, so the transfers overlap the
 // solve CTA by CTA and no copy is ever enqueued.  All accesses of the kernel to these
@@ -1026,6 +1066,8 @@ int cmpc_solve_host(cmpc_handle* h, int32_t B, int32_t slot0, const float* x0, c
   DEVICE_GUARD(h);
   const int N = h->cfg.N;
   Staging& st = h->st;
+  rc = flush_results(h);      // an asynchronous submission may still owe its result copies
+  if (rc) return rc;
   if (h->cfg.host_zero_copy) {
     rc = enqueue_zero_copy(h, B, slot0, x0, r, mask, x_des, mu, U, X, iters, pri_res, dua_res, status);
     if (rc < 0) return rc;
@@ -1198,6 +1240,8 @@ int cmpc_solve_host_async(cmpc_handle* h, int32_t B, int32_t slot0, const float*
         }
       }
       char* dout = st.d_async_out[a];
+      rc = flush_results(h);        // the previous submission's result copies: behind this one's input copies
+      if (rc) return rc;
       if (t >= 2) CUDA_TRY(cudaStreamWaitEvent(ks, st.done[(t - 2) & 7], 0));   // its results have left this arena
       rc = solve_device(h, B, slot0, (const float*)(din + L.x0), (const float*)(din + L.r), (const uint8_t*)(din + L.mask),
                         (const float*)(din + L.xdes), (const float*)(din + L.mu), (float*)(dout + Lo.U),
@@ -1206,17 +1250,11 @@ int cmpc_solve_host_async(cmpc_handle* h, int32_t B, int32_t slot0, const float*
                         status ? (int32_t*)(dout + Lo.status) : nullptr, ks, false);
       if (rc) return rc;
       CUDA_TRY(cudaEventRecord(st.solved[a], ks));
-      CUDA_TRY(cudaStreamWaitEvent(st.d2h, st.solved[a], 0));
-      CUDA_TRY(cudaMemcpyAsync(U, dout + Lo.U, (size_t)B * 12 * N * 4, cudaMemcpyDeviceToHost, st.d2h));
-      if (X) CUDA_TRY(cudaMemcpyAsync(X, dout + Lo.X, (size_t)B * 13 * (N + 1) * 4, cudaMemcpyDeviceToHost, st.d2h));
-      if (iters) CUDA_TRY(cudaMemcpyAsync(iters, dout + Lo.iters, (size_t)B * 4, cudaMemcpyDeviceToHost, st.d2h));
-      if (pri_res) CUDA_TRY(cudaMemcpyAsync(pri_res, dout + Lo.pri, (size_t)B * 4, cudaMemcpyDeviceToHost, st.d2h));
-      if (dua_res) CUDA_TRY(cudaMemcpyAsync(dua_res, dout + Lo.dua, (size_t)B * 4, cudaMemcpyDeviceToHost, st.d2h));
-      if (status) CUDA_TRY(cudaMemcpyAsync(status, dout + Lo.status, (size_t)B * 4, cudaMemcpyDeviceToHost, st.d2h));
-      // completion of this submission = its results are in the caller's buffers
       cudaEvent_t& evd = st.done[t & 7];
       if (!evd) CUDA_TRY(cudaEventCreateWithFlags(&evd, cudaEventDisableTiming));
-      CUDA_TRY(cudaEventRecord(evd, st.d2h));
+      Staging::Pending& q = st.pending;
+      q.active = true; q.ticket = t; q.B = B; q.arena = a;
+      q.U = U; q.X = X; q.iters = iters; q.pri = pri_res; q.dua = dua_res; q.status = status;
       st.next_ticket++;
       *ticket = t;
       return CMPC_OK;
@@ -1226,6 +1264,8 @@ int cmpc_solve_host_async(cmpc_handle* h, int32_t B, int32_t slot0, const float*
     if (rc < 0) return rc;
     if (rc == 0) return fail(CMPC_ERR_UNSUPPORTED, "cmpc_solve_host_async needs page-locked buffers (use cmpc_solve_host)");
   }
+  rc = flush_results(h);      // tickets complete in submission order
+  if (rc) return rc;
   st.next_ticket++;
   cudaEvent_t& ev = st.done[t & 7];
   if (!ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1239,6 +1279,10 @@ int cmpc_host_wait(cmpc_handle* h, int32_t ticket) {
   Staging& st = h->st;
   if (ticket < 0 || ticket >= st.next_ticket) return fail(CMPC_ERR_INVALID, "unknown ticket %d", ticket);
   DEVICE_GUARD(h);
+  if (st.pending.active && st.pending.ticket <= ticket) {
+    const int rc = flush_results(h);
+    if (rc) return rc;
+  }
   if (st.next_ticket - ticket > 8) {     // its event was reused: submissions complete in order, wait for the oldest kept
     CUDA_TRY(cudaEventSynchronize(st.done[st.next_ticket & 7]));
     return CMPC_OK;

@@ -425,6 +425,17 @@ def run_ours(args):
         h2d_ms.append(ev0.elapsed_time(ev1))
     h2d_gbs = sum(t.numel() * t.element_size() for t in pinned) / (statistics.median(h2d_ms) * 1e-3) / 1e9
     del dst
+    d2h_src = torch.empty((B, N, 12), dtype=torch.float32, device=dev)       # one step's forces, the bulk of the results
+    d2h_dst = torch.empty((B, N, 12), dtype=torch.float32).pin_memory()
+    d2h_ms = []
+    for _ in range(5):
+        ev0.record()
+        d2h_dst.copy_(d2h_src, non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        d2h_ms.append(ev0.elapsed_time(ev1))
+    d2h_gbs = d2h_src.numel() * 4 / (statistics.median(d2h_ms) * 1e-3) / 1e9
+    del d2h_src, d2h_dst
     bufs = [(hin, hout)]
     for _ in range(2):        # three buffer sets: the host runs up to two submissions ahead of the wait
         bufs.append(([torch.from_numpy(a).clone().pin_memory().numpy() for a in hin],
@@ -580,7 +591,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": out_bytes,
                 "blocking_value": total / e2e_block_s_max,
                 "rank0_ms_per_step_of_the_repetitions": [round(r_ / args.steps * 1e3, 4) for r_ in reps],
-                "rank0_h2d_copy_engine_gbs": h2d_gbs,
+                "rank0_h2d_copy_engine_gbs": h2d_gbs, "rank0_d2h_copy_engine_gbs": d2h_gbs,
                 "note": "may exceed `value`: the device-resident steps are timed one by one with the L2 flushed in between, "
                         "the pipelined steps run back to back on inputs the copy engines have just delivered",
                 "rank0_host_us_per_submission": {"p50": float(np.percentile(submit_us, 50)), "p95": float(np.percentile(submit_us, 95)),
